@@ -1,0 +1,192 @@
+/*
+ * crf_sm100.h -- C ABI of libcrf_sm100.so: the NeWCRFs neural-window FC-CRF block, forward and backward,
+ * as hand-written CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary for ONE hot path of LuizGuzzo/Monocular_Depth_Estimation:
+ *   src/newcrf_layers.py:30-59    window_partition / window_reverse
+ *   src/newcrf_layers.py:110-149  WindowAttention.forward
+ *   src/newcrf_layers.py:195-257  CRFBlock.forward
+ *   src/newcrf_layers.py:323-363  BasicCRFLayer.forward  (shift mask at :332-350)
+ * and the autograd backward of those functions (the reference has no explicit backward code).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no C++ exceptions cross the boundary.
+ *   - every function returns 0 on success, non-zero on error; crf_last_error() returns the message
+ *     (thread-local).
+ *   - every device buffer (inputs, outputs, saved-for-backward, workspace) is allocated by the caller; the
+ *     library never allocates, frees or retains device memory between calls.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no hidden syncs.
+ *   - entry points are re-entrant (forward runs on the Python thread, backward on the autograd engine
+ *     thread); the device ordinal is taken from the descriptor, not from thread-local CUDA state.
+ *   - "tokens" are the B*H*W feature-map positions in natural (b, h, w) order; T = B*H*W.
+ */
+#ifndef CRF_SM100_H_
+#define CRF_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRF_ABI_VERSION 1
+
+enum { CRF_DT_F32 = 0, CRF_DT_BF16 = 1 };
+
+/* --------------------------------------------------------------------------------------------------------
+ * Problem descriptor of one CRFBlock call (replaces the Python attributes CRFBlock.{dim,num_heads,
+ * window_size,shift_size,H,W}, newcrf_layers.py:170-193, and the tensor metadata torch carries).
+ * Strides are in ELEMENTS of the tensor's dtype.
+ *   x : logical (B, H*W, C)      -- the reference passes a strided view of NCHW (newcrf_layers.py:426)
+ *   v : logical (B, H, W, C)     -- strided view of NCHW (newcrf_layers.py:427)
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct crf_block_desc {
+  int32_t B, H, W, C;
+  int32_t num_heads;
+  int32_t window;   /* 7 */
+  int32_t shift;    /* 0 or window/2 */
+  int32_t training; /* 1: keep everything backward needs in `saved` */
+  int32_t device;   /* CUDA device ordinal that owns every pointer */
+  int32_t x_dtype;  /* CRF_DT_* */
+  int32_t v_dtype;
+  int32_t v_preconverted; /* 1: `v` already is the bf16 token-major copy produced by crf_convert_v */
+  int64_t x_stride_b, x_stride_t, x_stride_c;
+  int64_t v_stride_b, v_stride_h, v_stride_w, v_stride_c;
+} crf_block_desc;
+
+/* fp32 parameters of one CRFBlock, names as in the reference state_dict. */
+typedef struct crf_block_params {
+  const float* norm1_w;  /* (C)      blocks.i.norm1.weight */
+  const float* norm1_b;  /* (C)      */
+  const float* qk_w;     /* (2C, C)  blocks.i.attn.qk.weight : first C rows -> q, last C rows -> k */
+  const float* qk_b;     /* (2C)     */
+  const float* rpb_table;/* (169,nH) blocks.i.attn.relative_position_bias_table */
+  const float* proj_w;   /* (C, C)   */
+  const float* proj_b;   /* (C)      */
+  const float* norm2_w;  /* (C)      */
+  const float* norm2_b;  /* (C)      */
+  const float* fc1_w;    /* (4C, C)  */
+  const float* fc1_b;    /* (4C)     */
+  const float* fc2_w;    /* (C, 4C)  */
+  const float* fc2_b;    /* (C)      */
+  float qk_scale;        /* head_dim^-0.5 unless overridden (newcrf_layers.py:83) */
+  float ln_eps;          /* 1e-5 */
+} crf_block_params;
+
+/* fp32 gradient outputs, same shapes as crf_block_params; the library ACCUMULATES (+=) into them, so the
+ * caller zero-fills (or passes .grad buffers directly). */
+typedef struct crf_block_grads {
+  float* norm1_w; float* norm1_b;
+  float* qk_w;    float* qk_b;
+  float* rpb_table;
+  float* proj_w;  float* proj_b;
+  float* norm2_w; float* norm2_b;
+  float* fc1_w;   float* fc1_b;
+  float* fc2_w;   float* fc2_b;
+} crf_block_grads;
+
+const char* crf_last_error(void);
+int crf_abi_version(void);
+
+/* Sizes (bytes) of the caller-allocated `saved` buffer (lives from forward to backward when training) and of
+ * the scratch workspaces for forward and backward. */
+int crf_block_sizes(const crf_block_desc* d, size_t* saved_bytes, size_t* ws_fwd_bytes, size_t* ws_bwd_bytes);
+
+/* One CRFBlock forward: y = block(x, v).   Replaces CRFBlock.forward (newcrf_layers.py:195-257) including
+ * WindowAttention.forward (:110-149), window_partition/window_reverse/torch.roll/F.pad (:212-249), the shift
+ * mask (:332-350, evaluated in closed form) and Mlp.forward (:21-27).
+ *   y : (B, H*W, C) fp32 contiguous. */
+int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, float* y,
+                  void* saved, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of crf_block_fwd.  x and v are the SAME buffers (and descriptor) that were passed to forward: x is
+ * re-read when it was fp32 token-major (otherwise forward kept a copy in `saved`), v when v_preconverted.
+ *   dy : (B, H*W, C) fp32 contiguous;  dx : (B, H*W, C) fp32 contiguous (overwritten)
+ *   dv : (B, H, W, C) fp32 contiguous; dv_accumulate != 0 -> dv += (both blocks of a layer share v) */
+int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, const float* dy,
+                  const void* saved, float* dx, float* dv, int dv_accumulate, const crf_block_grads* g, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* v (B,H,W,C), any strides, fp32/bf16 -> bf16 token-major (T, C) contiguous; done once per BasicCRFLayer
+ * because both blocks read the same v (newcrf_layers.py:352-357). Uses the v_* fields of the descriptor. */
+int crf_convert_v(const crf_block_desc* d, const void* v, void* v_bf16, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Stand-alone index-map entry points (bit-exact tests).
+ * crf_window_gather  == F.pad -> torch.roll(-shift) -> window_partition   (newcrf_layers.py:215-233, :30-42)
+ * crf_window_scatter == window_reverse -> torch.roll(+shift) -> crop       (newcrf_layers.py:239-249, :45-59)
+ * crf_shift_mask     == the attn_mask BasicCRFLayer.forward builds         (newcrf_layers.py:332-350)
+ *   x       : (B, H, W, C) fp32 contiguous
+ *   windows : (B*nW, window*window, C) fp32 contiguous
+ *   mask    : (nW, N, N) fp32, N = window*window, values 0 / -100
+ * ------------------------------------------------------------------------------------------------------ */
+int crf_window_gather(const float* x, float* windows, int B, int H, int W, int C, int window, int shift,
+                      void* stream);
+int crf_window_scatter(const float* windows, float* x, int B, int H, int W, int C, int window, int shift,
+                       void* stream);
+int crf_shift_mask(float* mask, int H, int W, int window, int shift, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Stage-level entry points (unit tests and profiling of the individual kernels).
+ * ------------------------------------------------------------------------------------------------------ */
+enum {
+  CRF_EPI_STORE_F32 = 0,   /* out0 f32 = acc (+ bias)                                          */
+  CRF_EPI_STORE_BF16 = 1,  /* out0 bf16 = (acc + bias) * (n < scale_cols ? scale : 1)           */
+  CRF_EPI_BIAS_RES_F32 = 2,/* out0 f32 = acc + bias + res(aux1 f32)                             */
+  CRF_EPI_BIAS_GELU = 3,   /* out0 bf16 = pre = acc + bias (optional), out1 bf16 = gelu(pre)    */
+  CRF_EPI_MUL_DGELU = 4,   /* out0 bf16 = acc * gelu'(pre), pre = aux1 bf16                     */
+  CRF_EPI_ATOMIC_F32 = 5   /* out0 f32 += acc (split-K weight gradients)                        */
+};
+
+/* D[M,N] = sum_k A(m,k) * B(n,k) on tcgen05 (bf16 operands, fp32 accumulate in TMEM), TMA-fed.
+ * Each operand is a row-major bf16 matrix in one of two orientations:
+ *   major 0 (K-major) : stored (MN, K)   -- e.g. activations (tokens, channels), nn.Linear weight (out,in)
+ *   major 1 (MN-major): stored (K, MN)   -- e.g. weight (out,in) contracted over `out`, or (tokens, ch)
+ *                                           contracted over tokens (weight gradients) */
+typedef struct crf_gemm_args {
+  const void* A; const void* B;
+  int32_t a_major, b_major;
+  int32_t M, N, K;
+  int32_t epilogue;
+  int32_t split_k;         /* >= 1; only with CRF_EPI_ATOMIC_F32 */
+  void* out0; void* out1;
+  const float* bias;       /* (N) or NULL */
+  const void* aux1;        /* residual f32 (M,N) or pre bf16 (M,N) */
+  int64_t ld_out;          /* row stride (elements) of out0/out1/aux1 */
+  float scale; int32_t scale_cols;
+  int32_t device;
+} crf_gemm_args;
+int crf_gemm(const crf_gemm_args* a, void* stream);
+
+/* LayerNorm forward over channels with a layout change: x (B, T_img, C) with arbitrary strides ->
+ * xn bf16 (T, C), stats f32 (T, 2) = (mean, rstd), optional contiguous f32 copy of x. */
+int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, int B, int T_img, int C,
+               const float* gamma, const float* beta, float eps, void* xn_bf16, float* stats, float* x_copy,
+               int device, void* stream);
+/* LayerNorm backward: dx = LN'(g) + dres; accumulates dgamma/dbeta (+=). g f32 (T,C), x f32 (T,C). */
+int crf_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres, float* dx,
+               void* dx_bf16, float* dgamma, float* dbeta, int T, int C, int device, void* stream);
+/* out[n] += sum_t g[t, n], g bf16 (T, N) */
+int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
+/* f32 -> bf16 contiguous */
+int crf_cast_bf16(const float* src, void* dst, int64_t n, int device, void* stream);
+
+/* Window-attention core (everything between the qk projection and the output projection).
+ *   qk   bf16 (T, 2C): q already multiplied by scale (cols [0,C)), k (cols [C,2C))
+ *   vb   bf16 (T, C)
+ *   o    bf16 (T, C)   attention output in token order (window_reverse + un-roll + crop applied)
+ *   lse  f32 (B*nW, nH, 64) row log-sum-exp (saved for backward)
+ *   qk_bias f32 (2C): q/k of zero-padded tokens are their bias (newcrf_layers.py:215,118) */
+int crf_attn_fwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
+                 const float* rpb_table, void* o, float* lse, void* stream);
+/*   dout bf16 (T, C); dqk bf16 (T, 2C) (dq includes the scale factor); dv f32 (T, C) (= or +=);
+ *   d_table f32 (169, nH) +=;  d_qk_bias f32 (2C) += (only the k half receives pad-token gradient) */
+int crf_attn_bwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
+                 const float* rpb_table, const float* lse, const void* dout, void* dqk, float* dv,
+                 int dv_accumulate, float* d_table, float* d_qk_bias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRF_SM100_H_ */

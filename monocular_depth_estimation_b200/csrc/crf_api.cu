@@ -1,0 +1,321 @@
+// extern "C" entry points of libcrf_sm100.so (see include/crf_sm100.h) and the per-block orchestration:
+// which kernels run, in what order, on which slices of the caller-provided `saved` / workspace buffers.
+#include "crf_host.h"
+#include "crf_window.cuh"
+
+namespace crf {
+namespace {
+
+inline size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// Layout of the `saved` buffer (forward products backward needs) -- offsets in bytes.
+struct SavedLayout {
+  size_t xc, stats1, xn1, qk, vb, lse, attn_o, x1, stats2, xn2, pre, act, wb_qk, wb_proj, wb_fc1, wb_fc2, total;
+};
+// Layout of the backward workspace.
+struct BwdLayout {
+  size_t dyb, dhpre, dxn, dx1, dx1b, dob, dqk, total;
+};
+
+bool x_is_plain(const crf_block_desc& d) {
+  const int64_t T_img = static_cast<int64_t>(d.H) * d.W;
+  return d.x_dtype == CRF_DT_F32 && d.x_stride_c == 1 && d.x_stride_t == d.C && d.x_stride_b == T_img * d.C;
+}
+
+SavedLayout saved_layout(const crf_block_desc& d) {
+  const size_t T = static_cast<size_t>(d.B) * d.H * d.W;
+  const size_t C = d.C;
+  WindowGeom gm(d.H, d.W, d.window, d.shift);
+  SavedLayout L{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
+  L.xc = take(x_is_plain(d) ? 0 : T * C * 4);
+  L.stats1 = take(T * 2 * 4);
+  L.xn1 = take(T * C * 2);
+  L.qk = take(T * 2 * C * 2);
+  L.vb = take(d.v_preconverted ? 0 : T * C * 2);
+  L.lse = take(static_cast<size_t>(d.B) * gm.nW * d.num_heads * 64 * 4);
+  L.attn_o = take(T * C * 2);
+  L.x1 = take(T * C * 4);
+  L.stats2 = take(T * 2 * 4);
+  L.xn2 = take(T * C * 2);
+  L.pre = take(d.training ? T * 4 * C * 2 : 0);
+  L.act = take(T * 4 * C * 2);
+  L.wb_qk = take(2 * C * C * 2);
+  L.wb_proj = take(C * C * 2);
+  L.wb_fc1 = take(4 * C * C * 2);
+  L.wb_fc2 = take(4 * C * C * 2);
+  L.total = o;
+  return L;
+}
+
+BwdLayout bwd_layout(const crf_block_desc& d) {
+  const size_t T = static_cast<size_t>(d.B) * d.H * d.W;
+  const size_t C = d.C;
+  BwdLayout L{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
+  L.dyb = take(T * C * 2);
+  L.dhpre = take(T * 4 * C * 2);
+  L.dxn = take(T * C * 4);
+  L.dx1 = take(T * C * 4);
+  L.dx1b = take(T * C * 2);
+  L.dob = take(T * C * 2);
+  L.dqk = take(T * 2 * C * 2);
+  L.total = o;
+  return L;
+}
+
+int check_desc(const crf_block_desc* d) {
+  CRF_CHECK(d != nullptr, "null descriptor");
+  CRF_CHECK(d->B > 0 && d->H > 0 && d->W > 0, "empty input (B=%d H=%d W=%d)", d->B, d->H, d->W);
+  CRF_CHECK(d->C % 64 == 0 && d->C >= 64 && d->C <= 1024, "C=%d must be a multiple of 64 in [64,1024]", d->C);
+  CRF_CHECK(d->num_heads > 0 && d->C % d->num_heads == 0 && d->C / d->num_heads == 32,
+            "head_dim must be 32 (C=%d, heads=%d)", d->C, d->num_heads);
+  CRF_CHECK(d->window == 7, "window must be 7 (got %d)", d->window);
+  CRF_CHECK(d->shift >= 0 && d->shift < d->window, "shift_size must in 0-window_size");
+  CRF_CHECK(static_cast<int64_t>(d->B) * d->H * d->W * 4 * d->C < (int64_t(1) << 31) * 4,
+            "problem too large for 32-bit token indexing");
+  return 0;
+}
+
+int wgrad_splits(int M, int N, int K, int device) {
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  const int tiles = ((M + 127) / 128) * (N / BN);
+  const int chunks = (K + 63) / 64;
+  int s = (2 * num_sms(device) + tiles - 1) / tiles;
+  if (s > chunks) s = chunks;
+  if (s < 1) s = 1;
+  return s;
+}
+
+int gemm_fprop(const void* A, const void* W, int M, int N, int K, int epi, void* out0, void* out1, const float* bias,
+               const void* aux1, float scale, int scale_cols, int device, cudaStream_t st) {
+  crf_gemm_args a{};
+  a.A = A; a.B = W; a.a_major = 0; a.b_major = 0;
+  a.M = M; a.N = N; a.K = K; a.epilogue = epi; a.split_k = 1;
+  a.out0 = out0; a.out1 = out1; a.bias = bias; a.aux1 = aux1; a.ld_out = N;
+  a.scale = scale; a.scale_cols = scale_cols; a.device = device;
+  return launch_gemm(a, st);
+}
+// dX[M=T, N=Cin] = dY[T, K=Cout] * W[Cout, Cin]
+int gemm_dgrad(const void* dY, const void* W, int M, int N, int K, int epi, void* out0, const void* aux1, int device,
+               cudaStream_t st) {
+  crf_gemm_args a{};
+  a.A = dY; a.B = W; a.a_major = 0; a.b_major = 1;
+  a.M = M; a.N = N; a.K = K; a.epilogue = epi; a.split_k = 1;
+  a.out0 = out0; a.aux1 = aux1; a.ld_out = N; a.scale = 1.f; a.scale_cols = 0; a.device = device;
+  return launch_gemm(a, st);
+}
+// dW[M=Cout, N=Cin] += dY[T, Cout]^T * X[T, Cin]
+int gemm_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, int device, cudaStream_t st) {
+  crf_gemm_args a{};
+  a.A = dY; a.B = X; a.a_major = 1; a.b_major = 1;
+  a.M = M; a.N = N; a.K = K; a.epilogue = CRF_EPI_ATOMIC_F32; a.split_k = wgrad_splits(M, N, K, device);
+  a.out0 = dW; a.ld_out = N; a.scale = 1.f; a.device = device;
+  return launch_gemm(a, st);
+}
+
+}  // namespace
+}  // namespace crf
+
+using namespace crf;
+
+extern "C" {
+
+const char* crf_last_error(void) { return get_error(); }
+int crf_abi_version(void) { return CRF_ABI_VERSION; }
+
+int crf_block_sizes(const crf_block_desc* d, size_t* saved_bytes, size_t* ws_fwd_bytes, size_t* ws_bwd_bytes) {
+  if (check_desc(d)) return 1;
+  if (saved_bytes) *saved_bytes = saved_layout(*d).total;
+  if (ws_fwd_bytes) *ws_fwd_bytes = 256;  // forward needs no scratch beyond `saved`
+  if (ws_bwd_bytes) *ws_bwd_bytes = bwd_layout(*d).total;
+  return 0;
+}
+
+int crf_convert_v(const crf_block_desc* d, const void* v, void* v_bf16, void* stream) {
+  if (check_desc(d)) return 1;
+  CRF_CHECK(v != nullptr && v_bf16 != nullptr, "crf_convert_v: null pointer");
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  CRF_CHECK(d->v_stride_h == static_cast<int64_t>(d->W) * d->v_stride_w,
+            "crf_convert_v: v must be collapsible over (H, W): stride_h=%lld stride_w=%lld W=%d",
+            (long long)d->v_stride_h, (long long)d->v_stride_w, d->W);
+  return launch_convert_tokens(v, d->v_dtype, d->v_stride_b, d->v_stride_w, d->v_stride_c, d->B, d->H * d->W, d->C,
+                               v_bf16, static_cast<cudaStream_t>(stream));
+}
+
+int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, float* y,
+                  void* saved, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  if (check_desc(d)) return 1;
+  CRF_CHECK(p && x && v && y && saved, "crf_block_fwd: null pointer");
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SavedLayout L = saved_layout(*d);
+  uint8_t* S = static_cast<uint8_t*>(saved);
+  const int T = d->B * d->H * d->W, C = d->C;
+  const bool plain = x_is_plain(*d);
+
+  // bf16 operand copies of the four weight matrices (kept in `saved`: backward reuses them)
+  if (launch_cast_bf16(p->qk_w, S + L.wb_qk, 2LL * C * C, st)) return 1;
+  if (launch_cast_bf16(p->proj_w, S + L.wb_proj, 1LL * C * C, st)) return 1;
+  if (launch_cast_bf16(p->fc1_w, S + L.wb_fc1, 4LL * C * C, st)) return 1;
+  if (launch_cast_bf16(p->fc2_w, S + L.wb_fc2, 4LL * C * C, st)) return 1;
+
+  // LN1 (+ layout change of the NCHW view into token-major rows)
+  float* xc = plain ? nullptr : reinterpret_cast<float*>(S + L.xc);
+  if (launch_ln_fwd(x, d->x_dtype, d->x_stride_b, d->x_stride_t, d->x_stride_c, d->B, d->H * d->W, C, p->norm1_w,
+                    p->norm1_b, p->ln_eps, S + L.xn1, reinterpret_cast<float*>(S + L.stats1), xc, st))
+    return 1;
+  const float* x_tok = plain ? static_cast<const float*>(x) : xc;
+
+  const void* vb = v;
+  if (!d->v_preconverted) {
+    if (crf_convert_v(d, v, S + L.vb, stream)) return 1;
+    vb = S + L.vb;
+  }
+  // q (scaled) and k
+  if (gemm_fprop(S + L.xn1, S + L.wb_qk, T, 2 * C, C, CRF_EPI_STORE_BF16, S + L.qk, nullptr, p->qk_b, nullptr,
+                 p->qk_scale, C, d->device, st))
+    return 1;
+  // window attention core
+  if (launch_attn_fwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, S + L.attn_o,
+                      d->training ? reinterpret_cast<float*>(S + L.lse) : nullptr, st))
+    return 1;
+  // x1 = x + proj(attn)
+  if (gemm_fprop(S + L.attn_o, S + L.wb_proj, T, C, C, CRF_EPI_BIAS_RES_F32, S + L.x1, nullptr, p->proj_b, x_tok, 1.f,
+                 0, d->device, st))
+    return 1;
+  // LN2
+  if (launch_ln_fwd(S + L.x1, CRF_DT_F32, static_cast<int64_t>(d->H) * d->W * C, C, 1, d->B, d->H * d->W, C,
+                    p->norm2_w, p->norm2_b, p->ln_eps, S + L.xn2, reinterpret_cast<float*>(S + L.stats2), nullptr, st))
+    return 1;
+  // MLP
+  if (gemm_fprop(S + L.xn2, S + L.wb_fc1, T, 4 * C, C, CRF_EPI_BIAS_GELU, d->training ? S + L.pre : nullptr, S + L.act,
+                 p->fc1_b, nullptr, 1.f, 0, d->device, st))
+    return 1;
+  if (gemm_fprop(S + L.act, S + L.wb_fc2, T, C, 4 * C, CRF_EPI_BIAS_RES_F32, y, nullptr, p->fc2_b, S + L.x1, 1.f, 0,
+                 d->device, st))
+    return 1;
+  return 0;
+}
+
+int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, const float* dy,
+                  const void* saved, float* dx, float* dv, int dv_accumulate, const crf_block_grads* g, void* ws,
+                  size_t ws_bytes, void* stream) {
+  if (check_desc(d)) return 1;
+  CRF_CHECK(p && x && v && dy && saved && dx && dv && g && ws, "crf_block_bwd: null pointer");
+  CRF_CHECK(d->training, "crf_block_bwd: forward was not run with training=1");
+  const BwdLayout W = bwd_layout(*d);
+  CRF_CHECK(ws_bytes >= W.total, "crf_block_bwd: workspace too small (%zu < %zu)", ws_bytes, W.total);
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SavedLayout L = saved_layout(*d);
+  const uint8_t* S = static_cast<const uint8_t*>(saved);
+  uint8_t* Wk = static_cast<uint8_t*>(ws);
+  const int T = d->B * d->H * d->W, C = d->C, dev = d->device;
+  const bool plain = x_is_plain(*d);
+  const float* x_tok = plain ? static_cast<const float*>(x) : reinterpret_cast<const float*>(S + L.xc);
+  const void* vb = d->v_preconverted ? v : static_cast<const void*>(S + L.vb);
+  float* dxn = reinterpret_cast<float*>(Wk + W.dxn);
+  float* dx1 = reinterpret_cast<float*>(Wk + W.dx1);
+
+  // ---- MLP ----
+  if (launch_cast_bf16(dy, Wk + W.dyb, static_cast<int64_t>(T) * C, st)) return 1;
+  if (gemm_dgrad(Wk + W.dyb, S + L.wb_fc2, T, 4 * C, C, CRF_EPI_MUL_DGELU, Wk + W.dhpre, S + L.pre, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dyb, S + L.act, C, 4 * C, T, g->fc2_w, dev, st)) return 1;
+  if (launch_colsum_bf16(Wk + W.dyb, g->fc2_b, T, C, st)) return 1;
+  if (gemm_dgrad(Wk + W.dhpre, S + L.wb_fc1, T, C, 4 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, dev, st)) return 1;
+  if (launch_colsum_bf16(Wk + W.dhpre, g->fc1_b, T, 4 * C, st)) return 1;
+  if (launch_ln_bwd(dxn, reinterpret_cast<const float*>(S + L.x1), reinterpret_cast<const float*>(S + L.stats2),
+                    p->norm2_w, dy, dx1, Wk + W.dx1b, g->norm2_w, g->norm2_b, T, C, st))
+    return 1;
+  // ---- attention ----
+  if (gemm_dgrad(Wk + W.dx1b, S + L.wb_proj, T, C, C, CRF_EPI_STORE_BF16, Wk + W.dob, nullptr, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, dev, st)) return 1;
+  if (launch_colsum_bf16(Wk + W.dx1b, g->proj_b, T, C, st)) return 1;
+  if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, reinterpret_cast<const float*>(S + L.lse),
+                      Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st))
+    return 1;
+  if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, dev, st)) return 1;
+  if (launch_colsum_bf16(Wk + W.dqk, g->qk_b, T, 2 * C, st)) return 1;
+  if (launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, nullptr,
+                    g->norm1_w, g->norm1_b, T, C, st))
+    return 1;
+  return 0;
+}
+
+int crf_window_gather(const float* x, float* windows, int B, int H, int W, int C, int window, int shift,
+                      void* stream) {
+  CRF_CHECK(x && windows && B > 0 && H > 0 && W > 0 && C > 0 && window > 0, "crf_window_gather: bad arguments");
+  CRF_CHECK(shift >= 0 && shift < window, "shift_size must in 0-window_size");
+  return launch_window_gather(x, windows, B, H, W, C, window, shift, static_cast<cudaStream_t>(stream));
+}
+int crf_window_scatter(const float* windows, float* x, int B, int H, int W, int C, int window, int shift,
+                       void* stream) {
+  CRF_CHECK(x && windows && B > 0 && H > 0 && W > 0 && C > 0 && window > 0, "crf_window_scatter: bad arguments");
+  CRF_CHECK(shift >= 0 && shift < window, "shift_size must in 0-window_size");
+  return launch_window_scatter(windows, x, B, H, W, C, window, shift, static_cast<cudaStream_t>(stream));
+}
+int crf_shift_mask(float* mask, int H, int W, int window, int shift, void* stream) {
+  CRF_CHECK(mask && H > 0 && W > 0 && window > 0, "crf_shift_mask: bad arguments");
+  CRF_CHECK(shift >= 0 && shift < window, "shift_size must in 0-window_size");
+  return launch_shift_mask(mask, H, W, window, shift, static_cast<cudaStream_t>(stream));
+}
+
+int crf_gemm(const crf_gemm_args* a, void* stream) {
+  CRF_CHECK(a && a->A && a->B && a->out0, "crf_gemm: null pointer");
+  DeviceGuard guard(a->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", a->device);
+  return launch_gemm(*a, static_cast<cudaStream_t>(stream));
+}
+
+int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, int B, int T_img, int C,
+               const float* gamma, const float* beta, float eps, void* xn_bf16, float* stats, float* x_copy,
+               int device, void* stream) {
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_ln_fwd(x, x_dtype, sb, st, sc, B, T_img, C, gamma, beta, eps, xn_bf16, stats, x_copy,
+                       static_cast<cudaStream_t>(stream));
+}
+int crf_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres, float* dx,
+               void* dx_bf16, float* dgamma, float* dbeta, int T, int C, int device, void* stream) {
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_ln_bwd(g, x, stats, gamma, dres, dx, dx_bf16, dgamma, dbeta, T, C, static_cast<cudaStream_t>(stream));
+}
+int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream) {
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_colsum_bf16(g, out, T, N, static_cast<cudaStream_t>(stream));
+}
+int crf_cast_bf16(const float* src, void* dst, int64_t n, int device, void* stream) {
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_cast_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
+int crf_attn_fwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
+                 const float* rpb_table, void* o, float* lse, void* stream) {
+  if (check_desc(d)) return 1;
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  return launch_attn_fwd(*d, qk, vb, qk_bias, scale, rpb_table, o, lse, static_cast<cudaStream_t>(stream));
+}
+int crf_attn_bwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
+                 const float* rpb_table, const float* lse, const void* dout, void* dqk, float* dv,
+                 int dv_accumulate, float* d_table, float* d_qk_bias, void* stream) {
+  if (check_desc(d)) return 1;
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  return launch_attn_bwd(*d, qk, vb, qk_bias, scale, rpb_table, lse, dout, dqk, dv, dv_accumulate, d_table,
+                         d_qk_bias, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

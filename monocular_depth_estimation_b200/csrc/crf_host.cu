@@ -1,0 +1,66 @@
+// Host-side plumbing of libcrf_sm100.so: thread-local error string, TMA descriptor creation.
+#include "crf_host.h"
+
+#include <mutex>
+
+namespace crf {
+
+namespace {
+thread_local char g_err[512] = "";
+}
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+const char* get_error() { return g_err; }
+
+namespace {
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+      q == cudaDriverEntryPointSuccess)
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+}
+}  // namespace
+
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  std::call_once(g_encode_once, load_encode);
+  CRF_CHECK(g_encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  CRF_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: base pointer %p is not 16-byte aligned", ptr);
+  CRF_CHECK(cols % 8 == 0, "TMA: row pitch must be a multiple of 16 bytes (cols=%llu)", (unsigned long long)cols);
+  CRF_CHECK(box_rows >= 1 && box_rows <= 256, "TMA: box rows %u out of range", box_rows);
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CRF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
+            (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return 0;
+}
+
+int num_sms(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) return 148;
+  if (cached[device] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    cached[device] = n;
+  }
+  return cached[device];
+}
+
+}  // namespace crf

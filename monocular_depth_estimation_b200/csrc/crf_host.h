@@ -1,0 +1,72 @@
+// Host-side helpers shared by the translation units of libcrf_sm100.so: error reporting, device guard,
+// TMA tensor-map creation through the driver entry point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/crf_sm100.h"
+
+namespace crf {
+
+int set_error(const char* fmt, ...);  // always returns 1
+const char* get_error();
+
+#define CRF_CHECK(cond, ...)                  \
+  do {                                        \
+    if (!(cond)) return crf::set_error(__VA_ARGS__); \
+  } while (0)
+
+#define CRF_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return crf::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Sets the device for the duration of a call and restores the previous one (entry points may be called from
+// the autograd worker thread whose current device is not ours).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    cur = dev;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != cur) cudaSetDevice(prev);
+  }
+  int cur = -1;
+};
+
+// 2-D bf16 row-major tensor (rows, cols) -> tiled tensor map with 128-byte swizzle, box = (64 cols, box_rows).
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+int num_sms(int device);
+
+// ---- internal launchers (stream-ordered, no allocation) ----
+int launch_gemm(const crf_gemm_args& a, cudaStream_t st);
+int launch_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
+                  const float* gamma, const float* beta, float eps, void* xn, float* stats, float* x_copy,
+                  cudaStream_t st);
+int launch_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres,
+                  float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
+int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st);
+int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
+int launch_convert_tokens(const void* src, int dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
+                          void* dst_bf16, cudaStream_t st);
+int launch_window_gather(const float* x, float* windows, int B, int H, int W, int C, int window, int shift,
+                         cudaStream_t st);
+int launch_window_scatter(const float* windows, float* x, int B, int H, int W, int C, int window, int shift,
+                          cudaStream_t st);
+int launch_shift_mask(float* mask, int H, int W, int window, int shift, cudaStream_t st);
+int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
+                    const float* table, void* o, float* lse, cudaStream_t st);
+int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
+                    const float* table, const float* lse, const void* dout, void* dqk, float* dv, int dv_acc,
+                    float* d_table, float* d_qk_bias, cudaStream_t st);
+
+}  // namespace crf

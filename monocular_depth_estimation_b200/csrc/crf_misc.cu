@@ -1,0 +1,331 @@
+// Memory-bound helper kernels of the CRF block: LayerNorm forward (with the NCHW-view -> token-major layout
+// change folded in), LayerNorm backward (with the residual add and the gamma/beta reductions folded in), bias
+// gradient column sums, dtype casts, and the stand-alone window gather / scatter / mask used by the bit-exact
+// index tests.  All of these are HBM-bound: coalesced, vectorised accesses, warp-shuffle reductions.
+#include "crf_host.h"
+#include "crf_ptx.cuh"
+#include "crf_window.cuh"
+
+namespace crf {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward / plain conversion with layout change.
+// x logical (B, T_img, C), element (b,t,c) at b*sb + t*st + c*sc.  A CTA stages a 32-token x C tile in smem
+// (fp32), reading along whichever of (t, c) is contiguous, then one warp per token normalises and writes
+// token-major outputs.  DO_LN=false -> plain conversion (used for v).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnTok = 32;
+constexpr int kLnThreads = 256;
+
+template <typename TIn>
+__device__ __forceinline__ float load_as_float(const TIn* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+template <typename TIn, bool DO_LN>
+__global__ void __launch_bounds__(kLnThreads)
+ln_fwd_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int64_t sc, int T_img, int C,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+              __nv_bfloat16* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
+  extern __shared__ float tile[];  // [kLnTok][C + 1]
+  const int ldt = C + 1;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kLnTok;
+  const int nt = min(kLnTok, T_img - t0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TIn* xb = x + static_cast<int64_t>(b) * sb + static_cast<int64_t>(t0) * st;
+
+  if (sc == 1) {  // token rows are contiguous
+    for (int t = warp; t < nt; t += kLnThreads / 32)
+      for (int c = lane; c < C; c += 32) tile[t * ldt + c] = load_as_float<TIn>(xb + t * st + c);
+  } else {  // channel planes (NCHW view): tokens are contiguous (or generic strides)
+    for (int c = warp; c < C; c += kLnThreads / 32)
+      if (lane < nt) tile[lane * ldt + c] = load_as_float<TIn>(xb + lane * st + c * sc);
+  }
+  __syncthreads();
+
+  for (int t = warp; t < nt; t += kLnThreads / 32) {
+    const float* row = tile + t * ldt;
+    const int64_t tg = static_cast<int64_t>(b) * T_img + t0 + t;
+    float mean = 0.f, rstd = 1.f;
+    if (DO_LN) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += row[c];
+      mean = warp_sum(s) / C;
+      float q = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float d = row[c] - mean;
+        q += d * d;
+      }
+      rstd = rsqrtf(warp_sum(q) / C + eps);
+      if (lane == 0 && stats != nullptr) {
+        stats[2 * tg] = mean;
+        stats[2 * tg + 1] = rstd;
+      }
+    }
+    for (int c = 2 * lane; c < C; c += 64) {
+      float a0 = row[c], a1 = row[c + 1];
+      if (x_copy != nullptr) *reinterpret_cast<float2*>(x_copy + tg * C + c) = make_float2(a0, a1);
+      if (DO_LN) {
+        a0 = (a0 - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        a1 = (a1 - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+      }
+      *reinterpret_cast<uint32_t*>(xn + tg * C + c) = pack_bf16(a0, a1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  One warp per token row (grid-stride); each lane owns channels {2*lane + 64k, +1}.
+//   dx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat)) + dres
+//   dgamma += sum_t g * xhat,  dbeta += sum_t g
+// ------------------------------------------------------------------------------------------------
+template <int NCH>  // C = 64 * NCH
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
+              const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
+              __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, int T) {
+  constexpr int C = 64 * NCH;
+  __shared__ float red[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 gam[NCH], dga[NCH], dbe[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    gam[k] = __ldg(reinterpret_cast<const float2*>(gamma + 64 * k + 2 * lane));
+    dga[k] = make_float2(0.f, 0.f);
+    dbe[k] = make_float2(0.f, 0.f);
+  }
+  const int warps_total = gridDim.x * 8;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += warps_total) {
+    const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
+    const float* gr = g + static_cast<int64_t>(t) * C;
+    const float* xr = x + static_cast<int64_t>(t) * C;
+    float2 gv[NCH], xh[NCH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      gv[k] = __ldg(reinterpret_cast<const float2*>(gr + 64 * k + 2 * lane));
+      const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + 64 * k + 2 * lane));
+      xh[k] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
+      dga[k].x += gv[k].x * xh[k].x; dga[k].y += gv[k].y * xh[k].y;
+      dbe[k].x += gv[k].x;           dbe[k].y += gv[k].y;
+      gv[k].x *= gam[k].x;           gv[k].y *= gam[k].y;
+      s1 += gv[k].x + gv[k].y;
+      s2 += gv[k].x * xh[k].x + gv[k].y * xh[k].y;
+    }
+    s1 = warp_sum(s1) * (1.0f / C);
+    s2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      float o0 = rstd * (gv[k].x - s1 - xh[k].x * s2);
+      float o1 = rstd * (gv[k].y - s1 - xh[k].y * s2);
+      const int64_t off = static_cast<int64_t>(t) * C + 64 * k + 2 * lane;
+      if (dres != nullptr) {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(dres + off));
+        o0 += r.x; o1 += r.y;
+      }
+      *reinterpret_cast<float2*>(dx + off) = make_float2(o0, o1);
+      if (dx_bf16 != nullptr) *reinterpret_cast<uint32_t*>(dx_bf16 + off) = pack_bf16(o0, o1);
+    }
+  }
+  // cross-warp reduction of the per-lane partial column sums, then one atomic per column per CTA
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const float2 v = pass == 0 ? dga[k] : dbe[k];
+      red[warp][2 * lane] = v.x;
+      red[warp][2 * lane + 1] = v.y;
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        atomicAdd((pass == 0 ? dgamma : dbeta) + 64 * k + threadIdx.x, s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[n] += sum_t g[t,n], g bf16 (T,N).  Thread owns two adjacent columns; CTA covers 512 columns x a row chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out, int T, int N, int rows_per_cta) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(T, r0 + rows_per_cta);
+  float s0 = 0.f, s1 = 0.f;
+  const __nv_bfloat16* p = g + static_cast<int64_t>(r0) * N + c;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r, p += N) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    s0 += bf16_lo(w);
+    s1 += bf16_hi(w);
+  }
+  atomicAdd(out + c, s0);
+  atomicAdd(out + c + 1, s1);
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  } else {
+    for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone window gather / scatter / mask (bit-exact index tests)
+// ------------------------------------------------------------------------------------------------
+__global__ void window_gather_kernel(const float* __restrict__ x, float* __restrict__ win, WindowGeom gm, int C) {
+  const int bw = blockIdx.x;  // b * nW + window
+  const int b = bw / gm.nW, w = bw - b * gm.nW;
+  const int N = gm.ws * gm.ws;
+  for (int e = threadIdx.x; e < N * C; e += blockDim.x) {
+    const int p = e / C, c = e - p * C;
+    const int src = gm.source(w, p);
+    win[(static_cast<int64_t>(bw) * N + p) * C + c] =
+        src < 0 ? 0.f : x[(static_cast<int64_t>(b) * gm.H * gm.W + src) * C + c];
+  }
+}
+__global__ void window_scatter_kernel(const float* __restrict__ win, float* __restrict__ x, WindowGeom gm, int C) {
+  const int bw = blockIdx.x;
+  const int b = bw / gm.nW, w = bw - b * gm.nW;
+  const int N = gm.ws * gm.ws;
+  for (int e = threadIdx.x; e < N * C; e += blockDim.x) {
+    const int p = e / C, c = e - p * C;
+    const int dst = gm.source(w, p);
+    if (dst >= 0) x[(static_cast<int64_t>(b) * gm.H * gm.W + dst) * C + c] = win[(static_cast<int64_t>(bw) * N + p) * C + c];
+  }
+}
+__global__ void shift_mask_kernel(float* __restrict__ mask, WindowGeom gm) {
+  const int w = blockIdx.x;
+  const int N = gm.ws * gm.ws;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int i = e / N, j = e - i * N;
+    mask[static_cast<int64_t>(w) * N * N + e] = (gm.shift > 0 && gm.region(w, i) != gm.region(w, j)) ? -100.0f : 0.0f;
+  }
+}
+
+template <typename TIn>
+int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C, const float* gamma,
+                    const float* beta, float eps, void* xn, float* stats, float* x_copy, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(kLnTok) * (C + 1) * sizeof(float);
+  dim3 grid((T_img + kLnTok - 1) / kLnTok, B);
+  if (gamma != nullptr) {
+    auto k = ln_fwd_kernel<TIn, true>;
+    CRF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k<<<grid, kLnThreads, smem, st>>>(reinterpret_cast<const TIn*>(x), sb, st_, sc, T_img, C, gamma, beta, eps,
+                                      reinterpret_cast<__nv_bfloat16*>(xn), stats, x_copy);
+  } else {
+    auto k = ln_fwd_kernel<TIn, false>;
+    CRF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k<<<grid, kLnThreads, smem, st>>>(reinterpret_cast<const TIn*>(x), sb, st_, sc, T_img, C, nullptr, nullptr, eps,
+                                      reinterpret_cast<__nv_bfloat16*>(xn), nullptr, x_copy);
+  }
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
+                  const float* gamma, const float* beta, float eps, void* xn, float* stats, float* x_copy,
+                  cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "ln_fwd: C=%d must be a multiple of 64 in [64,1024]", C);
+  CRF_CHECK(gamma != nullptr && beta != nullptr, "ln_fwd: gamma/beta required");
+  if (x_dtype == CRF_DT_F32)
+    return launch_ln_fwd_t<float>(x, sb, st_, sc, B, T_img, C, gamma, beta, eps, xn, stats, x_copy, st);
+  if (x_dtype == CRF_DT_BF16)
+    return launch_ln_fwd_t<__nv_bfloat16>(x, sb, st_, sc, B, T_img, C, gamma, beta, eps, xn, stats, x_copy, st);
+  return set_error("ln_fwd: unsupported dtype %d", x_dtype);
+}
+
+int launch_convert_tokens(const void* src, int dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
+                          void* dst_bf16, cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "convert: C=%d must be a multiple of 64 in [64,1024]", C);
+  if (dtype == CRF_DT_F32)
+    return launch_ln_fwd_t<float>(src, sb, st_, sc, B, T_img, C, nullptr, nullptr, 0.f, dst_bf16, nullptr, nullptr, st);
+  if (dtype == CRF_DT_BF16)
+    return launch_ln_fwd_t<__nv_bfloat16>(src, sb, st_, sc, B, T_img, C, nullptr, nullptr, 0.f, dst_bf16, nullptr,
+                                          nullptr, st);
+  return set_error("convert: unsupported dtype %d", dtype);
+}
+
+int launch_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres,
+                  float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0, "ln_bwd: C=%d must be a multiple of 64", C);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int blocks = (T + 7) / 8;
+  const int cap = num_sms(dev) * 8;
+  if (blocks > cap) blocks = cap;
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define CRF_LNB(NCH)                                                                                         \
+  case NCH:                                                                                                  \
+    ln_bwd_kernel<NCH><<<blocks, 256, 0, st>>>(g, x, stats, gamma, dres, dx, dxb, dgamma, dbeta, T);         \
+    break;
+  switch (C / 64) {
+    CRF_LNB(1) CRF_LNB(2) CRF_LNB(4) CRF_LNB(8) CRF_LNB(16)
+    default: return set_error("ln_bwd: unsupported C=%d", C);
+  }
+#undef CRF_LNB
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st) {
+  CRF_CHECK(N % 2 == 0, "colsum: N must be even");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int gx = (N / 2 + 255) / 256;
+  int gy = (num_sms(dev) * 4 + gx - 1) / gx;
+  int rows = (T + gy - 1) / gy;
+  if (rows < 32) rows = 32;
+  gy = (T + rows - 1) / rows;
+  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int64_t threads = (n + 3) / 4;
+  cast_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_window_gather(const float* x, float* windows, int B, int H, int W, int C, int window, int shift,
+                         cudaStream_t st) {
+  WindowGeom gm(H, W, window, shift);
+  window_gather_kernel<<<B * gm.nW, 256, 0, st>>>(x, windows, gm, C);
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_window_scatter(const float* windows, float* x, int B, int H, int W, int C, int window, int shift,
+                          cudaStream_t st) {
+  WindowGeom gm(H, W, window, shift);
+  window_scatter_kernel<<<B * gm.nW, 256, 0, st>>>(windows, x, gm, C);
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_shift_mask(float* mask, int H, int W, int window, int shift, cudaStream_t st) {
+  WindowGeom gm(H, W, window, shift);
+  shift_mask_kernel<<<gm.nW, 256, 0, st>>>(mask, gm);
+  CRF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace crf
