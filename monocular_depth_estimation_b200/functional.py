@@ -1,0 +1,118 @@
+"""torch.autograd bridge to the C ABI: one C call per CRFBlock forward, one per backward.
+
+`crf_block(x, v, ...)` is the functional form of the reference's CRFBlock.forward
+(/root/reference/src/newcrf_layers.py:195-257).  PyTorch is used for device memory (every buffer the library
+touches is a torch tensor allocated here), the current CUDA stream and autograd bookkeeping -- nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .ops import make_desc
+
+# order of the parameter tensors in every call (matches _lib.PARAM_NAMES / crf_block_params)
+PARAM_KEYS = ("norm1.weight", "norm1.bias", "attn.qk.weight", "attn.qk.bias", "attn.relative_position_bias_table",
+              "attn.proj.weight", "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+              "mlp.fc2.weight", "mlp.fc2.bias")
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _param_struct(params, qk_scale, eps):
+    ps = L.BlockParams()
+    for name, t in zip(L.PARAM_NAMES, params):
+        setattr(ps, name, t.data_ptr())
+    ps.qk_scale = float(qk_scale)
+    ps.ln_eps = float(eps)
+    return ps
+
+
+def _sizes(desc):
+    s, f, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    L.check(L.lib().crf_block_sizes(C.byref(desc), C.byref(s), C.byref(f), C.byref(b)), "crf_block_sizes")
+    return s.value, f.value, b.value
+
+
+def convert_v(v: torch.Tensor) -> torch.Tensor:
+    """(B, H, W, C) fp32/bf16 with NCHW-view or contiguous strides -> bf16 (B*H*W, C).  No autograd."""
+    from .ops import convert_v as _cv
+    return _cv(v.detach())
+
+
+class _CRFBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, vb, H, W, num_heads, window, shift, qk_scale, eps, *params):
+        B, Ltok, Cd = x.shape
+        dev = x.device
+        params = tuple(p.detach().contiguous() for p in params)
+        training = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        xd = x.detach()
+        if vb is not None:
+            v_arg, desc = vb, make_desc(B, H, W, Cd, num_heads, shift, window=window, training=training,
+                                        device=dev.index, x=xd, v_preconverted=1)
+        else:
+            v_arg = v.detach()
+            if v_arg.stride(1) != W * v_arg.stride(2):
+                v_arg = v_arg.contiguous()
+            desc = make_desc(B, H, W, Cd, num_heads, shift, window=window, training=training, device=dev.index,
+                             x=xd, v=v_arg)
+        saved_bytes, _, ws_bwd = _sizes(desc)
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        y = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
+        ps = _param_struct(params, qk_scale, eps)
+        L.check(L.lib().crf_block_fwd(C.byref(desc), C.byref(ps), xd.data_ptr(), v_arg.data_ptr(), y.data_ptr(),
+                                      saved.data_ptr(), None, 0, _stream_ptr(dev)), "crf_block_fwd")
+        if training:
+            ctx.save_for_backward(xd, v_arg, saved, *params)
+            ctx.desc = desc
+            ctx.scalars = (qk_scale, eps, ws_bwd, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xd, v_arg, saved, *params = ctx.saved_tensors
+        qk_scale, eps, ws_bwd, H, W = ctx.scalars
+        desc = ctx.desc
+        dev = xd.device
+        B, Ltok, Cd = xd.shape
+        dy = dy.contiguous().float()
+        ws = torch.empty(ws_bwd, dtype=torch.uint8, device=dev)
+        dx = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
+        dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
+        grads = [torch.zeros_like(p) for p in params]
+        gs = L.BlockGrads()
+        for name, t in zip(L.PARAM_NAMES, grads):
+            setattr(gs, name, t.data_ptr())
+        ps = _param_struct(params, qk_scale, eps)
+        L.check(L.lib().crf_block_bwd(C.byref(desc), C.byref(ps), xd.data_ptr(), v_arg.data_ptr(), dy.data_ptr(),
+                                      saved.data_ptr(), dx.data_ptr(), dv.data_ptr(), 0, C.byref(gs), ws.data_ptr(),
+                                      ws.numel(), _stream_ptr(dev)), "crf_block_bwd")
+        return (dx, dv, None, None, None, None, None, None, None, None, *grads)
+
+
+def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None, eps=1e-5, v_bf16=None):
+    """One CRF block: LN1 -> (shifted-)window attention with q,k from x and v used raw -> +x -> LN2 -> MLP -> +.
+
+    x: (B, H*W, C) fp32/bf16, any strides (the reference hands over a view of NCHW); v: (B, H, W, C);
+    params: 13 fp32 tensors in PARAM_KEYS order; v_bf16: optional result of convert_v(v) shared between blocks.
+    Returns (B, H*W, C) fp32.  Mirrors the reference's error behaviour (newcrf_layers.py:205,143,180).
+    """
+    assert x.dim() == 3 and v.dim() == 4
+    B, Ltok, Cd = x.shape
+    assert Ltok == H * W, "input feature has wrong size"
+    assert Cd == v.shape[-1], "self.dim != v.shape[-1]"
+    assert 0 <= shift < window, "shift_size must in 0-window_size"
+    if not x.is_cuda:
+        raise RuntimeError("monocular_depth_estimation_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if v.dtype not in (torch.float32, torch.bfloat16):
+        v = v.float()
+    if qk_scale is None:
+        qk_scale = (Cd // num_heads) ** -0.5
+    return _CRFBlockFn.apply(x, v, v_bf16, H, W, num_heads, window, shift, float(qk_scale), float(eps), *params)

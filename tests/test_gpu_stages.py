@@ -1,0 +1,288 @@
+"""Stage-level parity tests of the individual sm_100a kernels, called through the C ABI (ctypes) and compared with
+plain PyTorch fp32 references of the same op evaluated on the same (bf16-rounded) inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import crf_oracle as O
+from tests.helpers import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from monocular_depth_estimation_b200 import ops
+    return ops
+
+
+def _L():
+    from monocular_depth_estimation_b200 import _lib
+    return _lib
+
+
+def _block_err_map(got, ref, bm=32, bn=32):
+    """Coarse map of max |err| per (bm x bn) block -- tells which tile / k-slice of a GEMM went wrong."""
+    e = (got.double() - ref.double()).abs()
+    M, N = e.shape
+    Mp, Np = -(-M // bm) * bm, -(-N // bn) * bn
+    pad = torch.zeros(Mp, Np, dtype=e.dtype, device=e.device)
+    pad[:M, :N] = e
+    m = pad.reshape(Mp // bm, bm, Np // bn, bn).amax(dim=(1, 3))
+    return np.array2string(m.cpu().numpy()[:12, :12], precision=2, max_line_width=200)
+
+
+def _check(got, ref, tol, what):
+    err = rel_l2(got, ref)
+    assert err < tol and torch.isfinite(got.float()).all(), (
+        f"{what}: rel_l2={err:.3e} (tol {tol:g})\nblock max-abs-error map (first 12x12 blocks of 32x32):\n"
+        + (_block_err_map(got.reshape(-1, got.shape[-1]), ref.reshape(-1, ref.shape[-1])) if got.dim() >= 2 else ""))
+
+
+DEV = "cuda"
+
+
+def _rand_bf16(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GEMM: the three operand orientations
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 128), (1000, 256, 512), (257, 64, 192),
+                                   (4800, 512, 128), (640, 1024, 256), (384, 128, 2048), (200, 256, 4096)])
+def test_gemm_fprop(M, N, K):
+    ops, L = _ops(), _L()
+    A, W = _rand_bf16(M, K, seed=1), _rand_bf16(N, K, seed=2, scale=K ** -0.5)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(A, W, M, N, K, a_major=0, b_major=0, epilogue=L.EPI_STORE_F32, out0=out)
+    torch.cuda.synchronize()
+    _check(out, A.float() @ W.float().t(), 1e-5, f"fprop {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 128), (1000, 512, 128), (257, 128, 512),
+                                   (640, 256, 1024), (500, 2048, 512)])
+def test_gemm_dgrad(M, N, K):
+    """dX = dY (M,K) @ W (K,N): B operand read MN-major from the (out,in) weight."""
+    ops, L = _ops(), _L()
+    A, W = _rand_bf16(M, K, seed=3), _rand_bf16(K, N, seed=4, scale=K ** -0.5)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(A, W, M, N, K, a_major=0, b_major=1, epilogue=L.EPI_STORE_F32, out0=out)
+    torch.cuda.synchronize()
+    _check(out, A.float() @ W.float(), 1e-5, f"dgrad {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K,split", [(128, 64, 64, 1), (128, 128, 1000, 1), (512, 128, 1000, 4),
+                                         (64, 256, 333, 3), (256, 512, 4800, 16), (1024, 256, 2400, 8)])
+def test_gemm_wgrad(M, N, K, split):
+    """dW (M,N) += dY (K,M)^T @ X (K,N): both operands MN-major, split-K over tokens with fp32 atomics."""
+    ops, L = _ops(), _L()
+    A, B = _rand_bf16(K, M, seed=5), _rand_bf16(K, N, seed=6, scale=K ** -0.5)
+    out = torch.zeros(M, N, device=DEV)
+    ops.gemm(A, B, M, N, K, a_major=1, b_major=1, epilogue=L.EPI_ATOMIC_F32, out0=out, split_k=split)
+    torch.cuda.synchronize()
+    _check(out, A.float().t() @ B.float(), 1e-5, f"wgrad {M}x{N}x{K} split {split}")
+
+
+def test_gemm_epilogues():
+    ops, L = _ops(), _L()
+    M, N, K = 333, 256, 128
+    A, W = _rand_bf16(M, K, seed=7), _rand_bf16(N, K, seed=8, scale=K ** -0.5)
+    bias = torch.randn(N, device=DEV)
+    acc = A.float() @ W.float().t()
+    # bf16 store with bias and a scale on the first 128 columns (the q half of the qk projection)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, M, N, K, epilogue=L.EPI_STORE_BF16, out0=out, bias=bias, scale=0.25, scale_cols=128)
+    ref = acc + bias
+    ref[:, :128] *= 0.25
+    _check(out.float(), ref, 4e-3, "store_bf16")
+    # bias + residual, fp32
+    res = torch.randn(M, N, device=DEV)
+    out = torch.zeros(M, N, device=DEV)
+    ops.gemm(A, W, M, N, K, epilogue=L.EPI_BIAS_RES_F32, out0=out, bias=bias, aux1=res)
+    _check(out, acc + bias + res, 1e-5, "bias_res_f32")
+    # bias + exact GELU, both pre- and post-activation
+    pre = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    act = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, M, N, K, epilogue=L.EPI_BIAS_GELU, out0=pre, out1=act, bias=bias)
+    _check(pre.float(), acc + bias, 4e-3, "gelu.pre")
+    _check(act.float(), F.gelu(acc + bias), 4e-3, "gelu.act")
+    # multiply by gelu'(pre)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, M, N, K, epilogue=L.EPI_MUL_DGELU, out0=out, aux1=pre)
+    p = pre.float().requires_grad_(True)
+    F.gelu(p).sum().backward()
+    _check(out.float(), acc * p.grad, 4e-3, "mul_dgelu")
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LayerNorm / conversions / reductions
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [64, 128, 512, 1024])
+@pytest.mark.parametrize("layout", ["nchw_view", "contig", "bf16_nchw"])
+def test_ln_fwd(C, layout):
+    ops = _ops()
+    B, H, W = 2, 9, 10
+    g = torch.Generator().manual_seed(C)
+    base = torch.randn(B, C, H, W, generator=g).to(DEV) * 2 + 0.5
+    if layout == "contig":
+        x = base.flatten(2).transpose(1, 2).contiguous()
+    elif layout == "bf16_nchw":
+        x = base.to(torch.bfloat16).flatten(2).transpose(1, 2)
+    else:
+        x = base.flatten(2).transpose(1, 2)
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    xn, stats, cp = ops.ln_fwd(x, gamma, beta, 1e-5, want_copy=True)
+    torch.cuda.synchronize()
+    xf = x.float().reshape(-1, C)
+    assert torch.equal(cp, xf.contiguous()), "fp32 copy must be bit-exact"
+    ref = F.layer_norm(xf, (C,), gamma, beta, 1e-5)
+    _check(xn.float(), ref, 4e-3, "ln_fwd.xn")
+    _check(stats[:, 0], xf.mean(-1), 1e-5, "ln_fwd.mean")
+    _check(stats[:, 1], (xf.var(-1, unbiased=False) + 1e-5).rsqrt(), 1e-5, "ln_fwd.rstd")
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512, 1024])
+def test_ln_bwd(C):
+    ops = _ops()
+    T = 777
+    g = torch.Generator().manual_seed(C + 1)
+    x = (torch.randn(T, C, generator=g) * 2 + 0.3).to(DEV).requires_grad_(True)
+    gamma = torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+    beta = torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(T, C, generator=g).to(DEV)
+    dres = torch.randn(T, C, generator=g).to(DEV)
+    y = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    y.backward(go)
+    xd = x.detach()
+    stats = torch.stack([xd.mean(-1), (xd.var(-1, unbiased=False) + 1e-5).rsqrt()], dim=1).contiguous()
+    dx, dxb, dgamma, dbeta = ops.ln_bwd(go, xd, stats, gamma.detach(), dres, want_bf16=True)
+    torch.cuda.synchronize()
+    _check(dx, x.grad + dres, 1e-5, "ln_bwd.dx")
+    _check(dxb.float(), x.grad + dres, 4e-3, "ln_bwd.dx_bf16")
+    _check(dgamma, gamma.grad, 1e-4, "ln_bwd.dgamma")
+    _check(dbeta, beta.grad, 1e-4, "ln_bwd.dbeta")
+
+
+def test_colsum_cast_convert():
+    ops = _ops()
+    gq = _rand_bf16(1234, 384, seed=11)
+    _check(ops.colsum_bf16(gq), gq.float().sum(0), 1e-5, "colsum")
+    src = torch.randn(100003, device=DEV)
+    assert torch.equal(ops.cast_bf16(src), src.to(torch.bfloat16))
+    v = torch.randn(2, 128, 9, 10, device=DEV).permute(0, 2, 3, 1)  # NCHW view, like newcrf_layers.py:427
+    assert torch.equal(ops.convert_v(v), v.reshape(-1, 128).to(torch.bfloat16))
+    v2 = torch.randn(2, 9, 10, 64, device=DEV)
+    assert torch.equal(ops.convert_v(v2), v2.reshape(-1, 64).to(torch.bfloat16))
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bit-exact index maps against the reference's own outputs (golden) and the oracle
+# ---------------------------------------------------------------------------------------------------------
+def test_window_index_maps_bit_exact():
+    ops = _ops()
+    g = load_golden("index_maps")
+    for H, W, s in g["cases"]:
+        H, W, s = int(H), int(W), int(s)
+        tag = f"{H}x{W}s{s}"
+        x = torch.arange(1, 2 * H * W * 3 + 1, dtype=torch.float32).reshape(2, H, W, 3).to(DEV)
+        win = ops.window_gather(x, 7, s)
+        assert np.array_equal(win.cpu().numpy(), g["gather." + tag]), tag
+        wv = torch.arange(1, win.numel() + 1, dtype=torch.float32).reshape(win.shape).to(DEV)
+        back = ops.window_scatter(wv, 2, H, W, 7, s)
+        assert np.array_equal(back.cpu().numpy(), g["scatter." + tag]), tag
+        if s == 3:
+            assert np.array_equal(ops.shift_mask(H, W, 7, s, DEV).cpu().numpy(), g["mask." + tag]), tag
+    # a large, padded, shifted case against the oracle (decoder scale 1/4 of a 480x640 input)
+    x = torch.randn(2, 120, 160, 8, device=DEV)
+    for s in (0, 3):
+        assert torch.equal(ops.window_gather(x, 7, s), O.window_gather(x, 7, s))
+        w = torch.randn(2 * 414, 49, 8, device=DEV)
+        assert torch.equal(ops.window_scatter(w, 2, 120, 160, 7, s), O.window_scatter(w, 2, 120, 160, 7, s))
+    assert np.array_equal(ops.shift_mask(120, 160, 7, 3, DEV).cpu().numpy(), O.shift_mask(120, 160, 7, 3))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# window-attention core
+# ---------------------------------------------------------------------------------------------------------
+def _attn_reference(qk, vb, qk_bias, table, B, H, W, C, nH, shift):
+    """fp32 reference of the attention core on the same bf16-rounded q/k/v, including the zero-pad-token rule
+    (k of a pad token = bias, v = 0) and the shift mask.  Differentiable w.r.t. qk, vb, table, qk_bias."""
+    N, hd = 49, C // nH
+    q = qk[:, :C].reshape(B, H, W, C)
+    k = qk[:, C:].reshape(B, H, W, C)
+    src = torch.from_numpy(O.window_source_index(H, W, 7, shift)).to(qk.device)
+    pad = (src < 0).reshape(1, -1, N, 1)
+    qw = O.window_gather(q, 7, shift)
+    kw = O.window_gather(k, 7, shift)
+    vw = O.window_gather(vb.reshape(B, H, W, C), 7, shift)
+    nW = src.shape[0]
+    kb = qk_bias[C:].to(torch.bfloat16).float() if not qk_bias.requires_grad else qk_bias[C:]
+    kw = torch.where(pad.expand(B, nW, N, C).reshape(B * nW, N, C), kb.expand(B * nW, N, C), kw)
+    qh = qw.reshape(-1, N, nH, hd).transpose(1, 2)
+    kh = kw.reshape(-1, N, nH, hd).transpose(1, 2)
+    vh = vw.reshape(-1, N, nH, hd).transpose(1, 2)
+    attn = qh @ kh.transpose(-2, -1)
+    idx = torch.from_numpy(O.relative_position_index(7)).to(qk.device)
+    attn = attn + table[idx.reshape(-1)].reshape(N, N, nH).permute(2, 0, 1).unsqueeze(0)
+    if shift > 0:
+        m = torch.from_numpy(O.shift_mask(H, W, 7, shift)).to(qk.device)
+        attn = (attn.reshape(B, nW, nH, N, N) + m[None, :, None]).reshape(-1, nH, N, N)
+    lse = torch.logsumexp(attn, dim=-1)
+    p = torch.softmax(attn, dim=-1)
+    ow = (p @ vh).transpose(1, 2).reshape(-1, N, C)
+    return O.window_scatter(ow, B, H, W, 7, shift).reshape(-1, C), lse
+
+
+ATTN_CASES = [(1, 7, 7, 64, 2, 0), (1, 14, 14, 64, 2, 0), (2, 9, 10, 64, 2, 0), (2, 9, 10, 64, 2, 3),
+              (1, 15, 20, 128, 4, 3), (3, 30, 40, 128, 4, 3), (2, 15, 20, 256, 8, 0), (1, 21, 16, 1024, 32, 3)]
+
+
+@pytest.mark.parametrize("B,H,W,C,nH,shift", ATTN_CASES)
+def test_attn_fwd(B, H, W, C, nH, shift):
+    ops = _ops()
+    T = B * H * W
+    qk = _rand_bf16(T, 2 * C, seed=21, scale=0.7)
+    vb = _rand_bf16(T, C, seed=22)
+    qk_bias = torch.randn(2 * C, device=DEV) * 0.5
+    table = torch.randn(169, nH, device=DEV) * 0.5
+    d = ops.make_desc(B, H, W, C, nH, shift, device=torch.cuda.current_device())
+    o, lse = ops.attn_fwd(d, qk, vb, qk_bias, (C // nH) ** -0.5, table)
+    torch.cuda.synchronize()
+    ref_o, ref_lse = _attn_reference(qk.float(), vb.float(), qk_bias, table, B, H, W, C, nH, shift)
+    _check(o.float(), ref_o, 1e-2, "attn_fwd.o")
+    _check(lse[:, :, :49], ref_lse, 1e-4, "attn_fwd.lse")
+
+
+@pytest.mark.parametrize("B,H,W,C,nH,shift", ATTN_CASES)
+def test_attn_bwd(B, H, W, C, nH, shift):
+    ops = _ops()
+    T = B * H * W
+    qk = _rand_bf16(T, 2 * C, seed=31, scale=0.7)
+    vb = _rand_bf16(T, C, seed=32)
+    dout = _rand_bf16(T, C, seed=33)
+    qk_bias = (torch.randn(2 * C, device=DEV) * 0.5).to(torch.bfloat16).float()
+    table = torch.randn(169, nH, device=DEV) * 0.5
+    scale = (C // nH) ** -0.5
+    d = ops.make_desc(B, H, W, C, nH, shift, device=torch.cuda.current_device())
+    o, lse = ops.attn_fwd(d, qk, vb, qk_bias, scale, table)
+    dqk, dv, d_table, d_bias = ops.attn_bwd(d, qk, vb, qk_bias, scale, table, lse, dout)
+    torch.cuda.synchronize()
+    qk_r = qk.float().requires_grad_(True)
+    vb_r = vb.float().requires_grad_(True)
+    tb_r = table.clone().requires_grad_(True)
+    bs_r = qk_bias.clone().requires_grad_(True)
+    ref_o, _ = _attn_reference(qk_r, vb_r, bs_r, tb_r, B, H, W, C, nH, shift)
+    ref_o.backward(dout.float())
+    ref_dqk = qk_r.grad.clone()
+    ref_dqk[:, :C] *= scale  # the kernel returns d(pre-scale q): q was stored pre-multiplied by scale
+    _check(dv, vb_r.grad, 1e-2, "attn_bwd.dv")
+    _check(dqk.float()[:, C:], ref_dqk[:, C:], 1.5e-2, "attn_bwd.dk")
+    _check(dqk.float()[:, :C], ref_dqk[:, :C], 1.5e-2, "attn_bwd.dq")
+    _check(d_table, tb_r.grad, 1.5e-2, "attn_bwd.d_table")
+    if bs_r.grad[C:].abs().max() > 0:
+        _check(d_bias[C:], bs_r.grad[C:], 1.5e-2, "attn_bwd.d_bias_k")
+    assert d_bias[:C].abs().max() == 0
