@@ -88,6 +88,8 @@ typedef struct crf_block_grads {
 
 const char* crf_last_error(void);
 int crf_abi_version(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+long long crf_kernel_launches(void);
 
 /* Sizes (bytes) of the caller-allocated `saved` buffer (lives from forward to backward when training) and of
  * the scratch workspaces for forward and backward. */

@@ -24,7 +24,7 @@ EPI_ATOMIC_F32 = 5
 
 # every symbol include/crf_sm100.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
-    "crf_last_error", "crf_abi_version", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
+    "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
     "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_ln_fwd", "crf_ln_bwd",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd",
 )
@@ -93,8 +93,10 @@ def _declare(lib):
     lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp]
     lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
-        if name != "crf_last_error":
+        if name not in ("crf_last_error", "crf_kernel_launches"):
             getattr(lib, name).restype = i32
+    lib.crf_kernel_launches.restype = C.c_longlong
+    lib.crf_kernel_launches.argtypes = []
 
 
 def lib():

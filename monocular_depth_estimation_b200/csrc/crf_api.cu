@@ -125,6 +125,7 @@ extern "C" {
 
 const char* crf_last_error(void) { return get_error(); }
 int crf_abi_version(void) { return CRF_ABI_VERSION; }
+long long crf_kernel_launches(void) { return launch_count(); }
 
 int crf_block_sizes(const crf_block_desc* d, size_t* saved_bytes, size_t* ws_fwd_bytes, size_t* ws_bwd_bytes) {
   if (check_desc(d)) return 1;

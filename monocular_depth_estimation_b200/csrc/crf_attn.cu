@@ -548,6 +548,7 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   if (gx < 1) gx = 1;
   attn_fwd_kernel<<<dim3(gx, P.nH), kAttnThreads, smem, st>>>(P);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -575,6 +576,7 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   if (gx < 1) gx = 1;
   attn_bwd_kernel<<<dim3(gx, P.nH), kAttnThreads, smem, st>>>(P);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

@@ -242,6 +242,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const crf_gemm_ar
   kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a.M, a.N, total_chunks, chunks_per_split, stages, a.a_major,
                                      a.b_major, ep);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

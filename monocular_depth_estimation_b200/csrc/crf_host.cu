@@ -1,6 +1,7 @@
 // Host-side plumbing of libcrf_sm100.so: thread-local error string, TMA descriptor creation.
 #include "crf_host.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace crf {
@@ -51,6 +52,12 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
             (unsigned long long)rows, (unsigned long long)cols, box_rows);
   return 0;
 }
+
+namespace {
+std::atomic<long long> g_launches{0};
+}
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms(int device) {
   static int cached[64] = {0};

@@ -46,6 +46,8 @@ struct DeviceGuard {
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 int num_sms(int device);
+void note_launch(int n = 1);   // kernel-launch counter exported as crf_kernel_launches()
+long long launch_count();
 
 // ---- internal launchers (stream-ordered, no allocation) ----
 int launch_gemm(const crf_gemm_args& a, cudaStream_t st);

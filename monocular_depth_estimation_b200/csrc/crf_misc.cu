@@ -234,6 +234,7 @@ int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, i
                                       reinterpret_cast<__nv_bfloat16*>(xn), nullptr, x_copy);
   }
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -281,6 +282,7 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
   }
 #undef CRF_LNB
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -295,6 +297,7 @@ int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st)
   gy = (T + rows - 1) / rows;
   colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -304,6 +307,7 @@ int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
   cast_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -312,6 +316,7 @@ int launch_window_gather(const float* x, float* windows, int B, int H, int W, in
   WindowGeom gm(H, W, window, shift);
   window_gather_kernel<<<B * gm.nW, 256, 0, st>>>(x, windows, gm, C);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int launch_window_scatter(const float* windows, float* x, int B, int H, int W, int C, int window, int shift,
@@ -319,12 +324,14 @@ int launch_window_scatter(const float* windows, float* x, int B, int H, int W, i
   WindowGeom gm(H, W, window, shift);
   window_scatter_kernel<<<B * gm.nW, 256, 0, st>>>(windows, x, gm, C);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int launch_shift_mask(float* mask, int H, int W, int window, int shift, cudaStream_t st) {
   WindowGeom gm(H, W, window, shift);
   shift_mask_kernel<<<gm.nW, 256, 0, st>>>(mask, gm);
   CRF_CUDA(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

@@ -50,7 +50,7 @@ class _CRFBlockFn(torch.autograd.Function):
         B, Ltok, Cd = x.shape
         dev = x.device
         params = tuple(p.detach().contiguous() for p in params)
-        training = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        training = any(ctx.needs_input_grad)  # all False under torch.no_grad()
         xd = x.detach()
         if vb is not None:
             v_arg, desc = vb, make_desc(B, H, W, Cd, num_heads, shift, window=window, training=training,

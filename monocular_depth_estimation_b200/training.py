@@ -1,0 +1,75 @@
+"""Training-step plumbing around the hot path: the reference loop's loss (src/train.py:89-100: SSIM + 0.1 * L1 on
+min-max-normalised depth; SSIM from src/loss.py:57-88) and the data-parallel wrapper the reference lacks
+(one process per GPU, NCCL gradient all-reduce over NVLink).  Windows never cross images, so sharding the batch
+needs no data-path collective; the only exchange is the parameter-gradient average, which DDP overlaps with backward.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def depth_norm(depth):
+    """src/utils.py:7-8 -- per-batch min-max normalisation."""
+    return (depth - depth.min()) / (depth.max() - depth.min())
+
+
+def ssim_loss(x, y):
+    """monodepth2-style SSIM on 3x3 average pools with reflection padding (src/loss.py:57-88)."""
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    x, y = F.pad(x, (1, 1, 1, 1), mode="reflect"), F.pad(y, (1, 1, 1, 1), mode="reflect")
+    mu_x, mu_y = F.avg_pool2d(x, 3, 1), F.avg_pool2d(y, 3, 1)
+    sx = F.avg_pool2d(x * x, 3, 1) - mu_x * mu_x
+    sy = F.avg_pool2d(y * y, 3, 1) - mu_y * mu_y
+    sxy = F.avg_pool2d(x * y, 3, 1) - mu_x * mu_y
+    n = (2 * mu_x * mu_y + c1) * (2 * sxy + c2)
+    d = (mu_x * mu_x + mu_y * mu_y + c1) * (sx + sy + c2)
+    return torch.clamp((1 - n / d) / 2, 0, 1).mean()
+
+
+def depth_loss(pred, depth_n):
+    """loss = 1.0 * SSIM + 0.1 * L1 (src/train.py:94-100)."""
+    return ssim_loss(pred, depth_n) + 0.1 * F.l1_loss(pred, depth_n)
+
+
+def init_distributed():
+    """One process per GPU (torchrun): returns (rank, local_rank, world_size, device)."""
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
+    if world > 1 and not dist.is_initialized():
+        if device.type == "cuda":
+            torch.cuda.set_device(device)
+            dist.init_process_group("nccl", device_id=device)
+        else:
+            dist.init_process_group("gloo")
+    return rank, local_rank, world, device
+
+
+def wrap_ddp(model, device, world):
+    """The DDP wrapper `train.py` lacks: gradients are averaged with an NCCL all-reduce, bucketed and launched while
+    backward is still running (crf3's 29 M parameters become ready first and are reduced under the rest)."""
+    if world <= 1:
+        return model
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    if device.type == "cuda":
+        return DDP(model, device_ids=[device.index], gradient_as_bucket_view=True, bucket_cap_mb=64)
+    return DDP(model)
+
+
+def train_step(model, optimizer, image, depth, autocast_dtype=torch.bfloat16):
+    """One iteration of the reference loop (src/train.py:86-114): forward, loss, zero_grad, backward, Adam step."""
+    depth_n = depth_norm(depth)
+    use_amp = autocast_dtype is not None and image.is_cuda
+    with torch.autocast("cuda", dtype=autocast_dtype, enabled=use_amp):
+        pred = model(image)
+    loss = depth_loss(pred.float(), depth_n)
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    optimizer.step()
+    return loss

@@ -1,0 +1,155 @@
+"""Parity of the fused CRF block / layer (CUDA path through the C ABI) with the reference: golden vectors produced by
+the unmodified reference module, and the oracle on seeded inputs at BASELINE.json config-1 and config-2 shapes.
+
+Tolerance: this is the bf16-I/O path (bf16 tensor-core operands and bf16 intermediates, fp32 accumulation, fp32
+residual stream, fp32 softmax/LayerNorm): BASELINE.json states rel 2e-2 for it, rel = ||a-b||_2 / ||b||_2.
+"""
+import pytest
+import torch
+
+from oracle import crf_oracle as O
+from tests.helpers import LAYER_CASES, golden_layer_inputs, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+DEV = "cuda"
+
+
+def _report(case, errs):
+    """Append the measured relative errors to gpurun_out/parity_errs.jsonl (evidence for DESIGN.md)."""
+    import json, os
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/parity_errs.jsonl", "a") as f:
+            f.write(json.dumps({"case": case, "max": max(errs.values()), "errs": errs}) + "\n")
+
+
+def _pkg():
+    import monocular_depth_estimation_b200 as pkg
+    return pkg
+
+
+def _layer_from_golden(g, C, nH, depth):
+    pkg = _pkg()
+    layer = pkg.BasicCRFLayer(dim=C, depth=depth, num_heads=nH, v_dim=C, window_size=7)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    missing, unexpected = layer.load_state_dict(sd, strict=True)   # drop-in: reference checkpoint keys load as-is
+    assert not missing and not unexpected
+    return layer.to(DEV)
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_layer_matches_reference_golden(name):
+    g = load_golden(name)
+    (B, H, W, C, nH, depth), x, v, _ = golden_layer_inputs(g, DEV)
+    layer = _layer_from_golden(g, C, nH, depth)
+    x = x.detach().requires_grad_(True)
+    v = v.detach().requires_grad_(True)
+    out = layer(x, v, H, W)
+    assert out[1] == H and out[2] == W and out[3] is out[0] and out[4] == H and out[5] == W
+    y = out[0]
+    assert y.shape == (B, H * W, C) and y.is_contiguous()
+    y.backward(torch.from_numpy(g["dy"]).to(DEV))
+    torch.cuda.synchronize()
+    errs = {"y": rel_l2(y.detach(), g["y"]), "dx": rel_l2(x.grad, g["dx"]), "dv": rel_l2(v.grad, g["dv"])}
+    for k, p in layer.named_parameters():
+        errs[k] = rel_l2(p.grad, g["grad." + k])
+    _report("golden " + name, errs)
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, f"rel_l2 above {TOL}: {bad}\nall: {errs}"
+
+
+def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device):
+    from monocular_depth_estimation_b200 import functional as CF
+    gen = torch.Generator().manual_seed(seed)
+    p = O.init_block_params(C, nH, gen)
+    if strided:
+        x = torch.randn(B, C, H, W, generator=gen).flatten(2).transpose(1, 2)
+        v = torch.randn(B, C, H, W, generator=gen).permute(0, 2, 3, 1)
+    else:
+        x = torch.randn(B, H * W, C, generator=gen)
+        v = torch.randn(B, H, W, C, generator=gen)
+    dy = torch.randn(B, H * W, C, generator=gen)
+    # oracle (fp32)
+    po = {k: t.detach().clone().to(oracle_device).requires_grad_(True) for k, t in p.items()}
+    xo = x.to(oracle_device).detach().requires_grad_(True)
+    vo = v.to(oracle_device).detach().requires_grad_(True)
+    yo = O.crf_block(xo, vo, H, W, po, nH, 7, shift)
+    yo.backward(dy.to(oracle_device))
+    # CUDA path
+    pc = {k: t.detach().clone().to(DEV).requires_grad_(True) for k, t in p.items()}
+    xc = x.to(DEV)
+    vc = v.to(DEV)
+    if strided:  # .to() keeps the permuted strides
+        assert not xc.is_contiguous()
+    xc = xc.detach().requires_grad_(True)
+    vc = vc.detach().requires_grad_(True)
+    yc = CF.crf_block(xc, vc, H, W, [pc[k] for k in CF.PARAM_KEYS], nH, window=7, shift=shift)
+    yc.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    errs = {"y": rel_l2(yc.detach(), yo.detach()), "dx": rel_l2(xc.grad, xo.grad), "dv": rel_l2(vc.grad, vo.grad)}
+    for k in CF.PARAM_KEYS:
+        errs[k] = rel_l2(pc[k].grad, po[k].grad)
+    _report(f"block B{B} {H}x{W} C{C} nH{nH} shift{shift} strided{int(strided)} oracle@{oracle_device}", errs)
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, f"rel_l2 above {TOL}: {bad}\nall: {errs}"
+    return errs
+
+
+@pytest.mark.parametrize("shift", [0, 3])
+@pytest.mark.parametrize("strided", [False, True])
+def test_config1_block_vs_oracle_cpu(shift, strided):
+    """BASELINE.json configs[0]: one CRFBlock fwd+bwd, window 7, C=128, 4 heads, 60x80 (1/4 of 240x320), batch 2."""
+    _run_block_vs_oracle(2, 60, 80, 128, 4, shift, seed=10 + shift, strided=strided, oracle_device="cpu")
+
+
+@pytest.mark.parametrize("H,W,C,nH", [(120, 160, 128, 4), (60, 80, 256, 8), (30, 40, 512, 16), (15, 20, 1024, 32)])
+@pytest.mark.parametrize("shift", [0, 3])
+def test_config2_stage_shapes_vs_oracle(H, W, C, nH, shift):
+    """The four decoder scales of configs[1] (480x640, batch 8).  The oracle is evaluated with torch on the GPU here
+    only because the fp32 CPU run of the 1/4 scale takes minutes; it is the same oracle code."""
+    _run_block_vs_oracle(8, H, W, C, nH, shift, seed=100 + C + shift, strided=True, oracle_device=DEV)
+
+
+def test_inference_path_matches_training_path():
+    pkg = _pkg()
+    torch.manual_seed(0)
+    layer = pkg.BasicCRFLayer(dim=128, depth=2, num_heads=4, v_dim=128).to(DEV)
+    x = torch.randn(2, 128, 30, 40, device=DEV).flatten(2).transpose(1, 2)
+    v = torch.randn(2, 128, 30, 40, device=DEV).permute(0, 2, 3, 1)
+    with torch.no_grad():
+        y0 = layer(x, v, 30, 40)[0]
+    y1 = layer(x.clone().requires_grad_(True), v, 30, 40)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1.detach())
+
+
+def test_bf16_inputs_and_autocast_like_usage():
+    """Under bf16 autocast the conv projections hand over bf16 NCHW views; output stays fp32 (residual stream)."""
+    pkg = _pkg()
+    torch.manual_seed(1)
+    layer = pkg.BasicCRFLayer(dim=64, depth=2, num_heads=2, v_dim=64).to(DEV)
+    xb = torch.randn(2, 64, 15, 20, device=DEV).to(torch.bfloat16)
+    vb = torch.randn(2, 64, 15, 20, device=DEV).to(torch.bfloat16)
+    x = xb.flatten(2).transpose(1, 2).requires_grad_(True)
+    v = vb.permute(0, 2, 3, 1).requires_grad_(True)
+    y = layer(x, v, 15, 20)[0]
+    assert y.dtype == torch.float32
+    y.square().mean().backward()
+    blocks = [{k: p.detach().float().cpu() for k, p in blk.state_dict().items()
+               if not k.endswith("relative_position_index")} for blk in layer.blocks]
+    yo = O.basic_crf_layer(xb.float().cpu().flatten(2).transpose(1, 2), vb.float().cpu().permute(0, 2, 3, 1), 15, 20,
+                           blocks, 2)
+    assert rel_l2(y.detach(), yo) < TOL
+    assert x.grad.dtype == torch.bfloat16 and torch.isfinite(x.grad.float()).all()
+
+
+def test_reference_error_behaviour():
+    pkg = _pkg()
+    blk = pkg.CRFBlock(64, 2, 64).to(DEV)
+    blk.H, blk.W = 5, 5
+    with pytest.raises(AssertionError, match="input feature has wrong size"):
+        blk(torch.randn(1, 24, 64, device=DEV), torch.randn(1, 5, 5, 64, device=DEV), None)
+    with pytest.raises(AssertionError, match="self.dim != v.shape"):
+        blk(torch.randn(1, 25, 64, device=DEV), torch.randn(1, 5, 5, 32, device=DEV), None)
+    with pytest.raises(AssertionError, match="shift_size must in 0-window_size"):
+        pkg.CRFBlock(64, 2, 64, window_size=7, shift_size=7)
