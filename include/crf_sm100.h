@@ -90,6 +90,11 @@ const char* crf_last_error(void);
 int crf_abi_version(void);
 /* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
 long long crf_kernel_launches(void);
+/* Per-kernel timing for bench.py's roofline: when enabled, every kernel launch is bracketed by CUDA events on its
+ * own stream.  crf_timing_report synchronises them and writes a JSON array (one object per kernel label: launches,
+ * total_ms, algorithmic flops and bytes per launch) into buf; returns the size needed.  Enabling clears old data. */
+int crf_timing_enable(int on);
+size_t crf_timing_report(char* buf, size_t cap);
 
 /* Sizes (bytes) of the caller-allocated `saved` buffer (lives from forward to backward when training) and of
  * the scratch workspaces for forward and backward. */

@@ -24,7 +24,7 @@ EPI_ATOMIC_F32 = 5
 
 # every symbol include/crf_sm100.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
-    "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
+    "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_timing_enable", "crf_timing_report", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
     "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_ln_fwd", "crf_ln_bwd",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd",
 )
@@ -93,10 +93,13 @@ def _declare(lib):
     lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp]
     lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
-        if name not in ("crf_last_error", "crf_kernel_launches"):
+        if name not in ("crf_last_error", "crf_kernel_launches", "crf_timing_report"):
             getattr(lib, name).restype = i32
     lib.crf_kernel_launches.restype = C.c_longlong
     lib.crf_kernel_launches.argtypes = []
+    lib.crf_timing_enable.argtypes = [i32]
+    lib.crf_timing_report.restype = sz
+    lib.crf_timing_report.argtypes = [C.c_char_p, sz]
 
 
 def lib():

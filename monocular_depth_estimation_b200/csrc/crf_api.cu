@@ -126,6 +126,8 @@ extern "C" {
 const char* crf_last_error(void) { return get_error(); }
 int crf_abi_version(void) { return CRF_ABI_VERSION; }
 long long crf_kernel_launches(void) { return launch_count(); }
+int crf_timing_enable(int on) { timing_enable(on != 0); return 0; }
+size_t crf_timing_report(char* buf, size_t cap) { return timing_report(buf, cap); }
 
 int crf_block_sizes(const crf_block_desc* d, size_t* saved_bytes, size_t* ws_fwd_bytes, size_t* ws_bwd_bytes) {
   if (check_desc(d)) return 1;

@@ -546,6 +546,9 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   int gx = (num_sms(d.device) * 4 + P.nH - 1) / P.nH;
   if (gx > P.npairs) gx = P.npairs;
   if (gx < 1) gx = 1;
+  const double TC = static_cast<double>(d.B) * d.H * d.W * d.C;
+  KernelTimer tm(st, 4.0 * 49 * 49 * d.C * P.total_windows, 8.0 * TC, "attn_fwd_B%d_%dx%d_C%d_s%d", d.B, d.H, d.W, d.C,
+                 d.shift);
   attn_fwd_kernel<<<dim3(gx, P.nH), kAttnThreads, smem, st>>>(P);
   CRF_CUDA(cudaGetLastError());
   note_launch();
@@ -574,6 +577,9 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   int gx = (num_sms(d.device) * 2 + P.nH - 1) / P.nH;
   if (gx > P.npairs) gx = P.npairs;
   if (gx < 1) gx = 1;
+  const double TC = static_cast<double>(d.B) * d.H * d.W * d.C;
+  KernelTimer tm(st, 10.0 * 49 * 49 * d.C * P.total_windows, 16.0 * TC, "attn_bwd_B%d_%dx%d_C%d_s%d", d.B, d.H, d.W,
+                 d.C, d.shift);
   attn_bwd_kernel<<<dim3(gx, P.nH), kAttnThreads, smem, st>>>(P);
   CRF_CUDA(cudaGetLastError());
   note_launch();

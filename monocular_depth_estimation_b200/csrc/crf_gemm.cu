@@ -239,6 +239,13 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const crf_gemm_ar
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   EpiParams ep{a.out0, a.out1, a.bias, a.aux1, a.ld_out, a.scale, a.scale_cols};
   dim3 grid((a.M + BM - 1) / BM, a.N / BN, splits);
+  const double mn = static_cast<double>(a.M) * a.N;
+  const double out_bytes = EPI == CRF_EPI_STORE_BF16 ? 2 * mn
+                           : EPI == CRF_EPI_BIAS_RES_F32 ? 8 * mn
+                           : EPI == CRF_EPI_BIAS_GELU ? (a.out0 != nullptr ? 4 * mn : 2 * mn)
+                           : 4 * mn;
+  KernelTimer tm(st, 2.0 * mn * a.K, 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
+                 "gemm_%s_epi%d_M%d_N%d_K%d", a.a_major ? "wgrad" : (a.b_major ? "dgrad" : "fprop"), EPI, a.M, a.N, a.K);
   kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a.M, a.N, total_chunks, chunks_per_split, stages, a.a_major,
                                      a.b_major, ep);
   CRF_CUDA(cudaGetLastError());

@@ -1,8 +1,13 @@
 // Host-side plumbing of libcrf_sm100.so: thread-local error string, TMA descriptor creation.
 #include "crf_host.h"
 
+#include <string.h>
+
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace crf {
 
@@ -58,6 +63,73 @@ std::atomic<long long> g_launches{0};
 }
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- per-kernel timing --------------------------------------------------------------------------
+namespace {
+struct TimingEntry {
+  double flops = 0, bytes = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+};
+std::mutex g_tm_mu;
+std::atomic<bool> g_timing{false};
+std::map<std::string, TimingEntry> g_tm;
+}  // namespace
+
+KernelTimer::KernelTimer(cudaStream_t st, double flops, double bytes, const char* fmt, ...)
+    : st_(st), flops_(flops), bytes_(bytes) {
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(label_, sizeof(label_), fmt, ap);
+  va_end(ap);
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) return;
+  on_ = true;
+  cudaEventRecord(e0_, st_);
+}
+KernelTimer::~KernelTimer() {
+  if (!on_) return;
+  cudaEventRecord(e1_, st_);
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  TimingEntry& e = g_tm[label_];
+  e.flops = flops_;
+  e.bytes = bytes_;
+  e.evs.emplace_back(e0_, e1_);
+}
+void timing_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  if (on) {
+    for (auto& kv : g_tm)
+      for (auto& p : kv.second.evs) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    g_tm.clear();
+  }
+  g_timing.store(on);
+}
+// JSON array: [{"kernel": label, "launches": n, "total_ms": t, "flops": per-launch, "bytes": per-launch}, ...]
+size_t timing_report(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  std::string out = "[";
+  bool first = true;
+  for (auto& kv : g_tm) {
+    double total = 0;
+    for (auto& p : kv.second.evs) {
+      cudaEventSynchronize(p.second);
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) total += ms;
+    }
+    char line[320];
+    snprintf(line, sizeof(line), "%s{\"kernel\": \"%s\", \"launches\": %zu, \"total_ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.evs.size(), total, kv.second.flops, kv.second.bytes);
+    out += line;
+    first = false;
+  }
+  out += "]";
+  if (buf != nullptr && cap > 0) {
+    const size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
+}
 
 int num_sms(int device) {
   static int cached[64] = {0};

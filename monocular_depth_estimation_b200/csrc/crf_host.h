@@ -46,7 +46,23 @@ struct DeviceGuard {
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 int num_sms(int device);
-void note_launch(int n = 1);   // kernel-launch counter exported as crf_kernel_launches()
+void note_launch(int n = 1);
+
+// Optional per-kernel timing (crf_timing_enable): CUDA events recorded on the launch stream around each kernel,
+// aggregated per label together with the kernel's ALGORITHMIC flops and bytes.  Off by default (zero overhead).
+class KernelTimer {
+ public:
+  KernelTimer(cudaStream_t st, double flops, double bytes, const char* fmt, ...);
+  ~KernelTimer();
+ private:
+  cudaStream_t st_;
+  cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+  double flops_, bytes_;
+  char label_[96];
+  bool on_ = false;
+};
+void timing_enable(bool on);
+size_t timing_report(char* buf, size_t cap);   // kernel-launch counter exported as crf_kernel_launches()
 long long launch_count();
 
 // ---- internal launchers (stream-ordered, no allocation) ----

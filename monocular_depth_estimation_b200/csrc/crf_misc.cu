@@ -222,6 +222,9 @@ int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, i
                     const float* beta, float eps, void* xn, float* stats, float* x_copy, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(kLnTok) * (C + 1) * sizeof(float);
   dim3 grid((T_img + kLnTok - 1) / kLnTok, B);
+  const double tc = static_cast<double>(B) * T_img * C;
+  KernelTimer tm(st, 0.0, tc * (sizeof(TIn) + 2 + (x_copy != nullptr ? 4 : 0)), "%s_T%d_C%d",
+                 gamma != nullptr ? "ln_fwd" : "convert_bf16", B * T_img, C);
   if (gamma != nullptr) {
     auto k = ln_fwd_kernel<TIn, true>;
     CRF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -272,6 +275,8 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
   const int cap = num_sms(dev) * 8;
   if (blocks > cap) blocks = cap;
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  KernelTimer tm(st, 0.0, static_cast<double>(T) * C * (12 + (dres != nullptr ? 4 : 0) + (dx_bf16 != nullptr ? 2 : 0)),
+                 "ln_bwd_T%d_C%d", T, C);
 #define CRF_LNB(NCH)                                                                                         \
   case NCH:                                                                                                  \
     ln_bwd_kernel<NCH><<<blocks, 256, 0, st>>>(g, x, stats, gamma, dres, dx, dxb, dgamma, dbeta, T);         \
@@ -295,6 +300,7 @@ int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st)
   int rows = (T + gy - 1) / gy;
   if (rows < 32) rows = 32;
   gy = (T + rows - 1) / rows;
+  KernelTimer tm(st, 0.0, 2.0 * T * N, "colsum_T%d_N%d", T, N);
   colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
   CRF_CUDA(cudaGetLastError());
   note_launch();
@@ -304,6 +310,7 @@ int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st)
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
   const int64_t threads = (n + 3) / 4;
+  KernelTimer tm(st, 0.0, 6.0 * n, "cast_bf16_n%lld", static_cast<long long>(n));
   cast_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   CRF_CUDA(cudaGetLastError());

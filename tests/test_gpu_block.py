@@ -153,3 +153,24 @@ def test_reference_error_behaviour():
         blk(torch.randn(1, 25, 64, device=DEV), torch.randn(1, 5, 5, 32, device=DEV), None)
     with pytest.raises(AssertionError, match="shift_size must in 0-window_size"):
         pkg.CRFBlock(64, 2, 64, window_size=7, shift_size=7)
+
+
+def test_full_model_dropin_matches_oracle_model():
+    """one state_dict, the oracle's full model on CPU (fp32) vs the product model on the GPU
+    (fp32 everywhere except the CRF blocks' bf16 tensor-core operands)."""
+    from monocular_depth_estimation_b200.model import PTModel
+    from oracle.model_oracle import OraclePTModel
+    torch.manual_seed(3)
+    ref = OraclePTModel().eval()
+    ours = PTModel().eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours = ours.to(DEV)
+    img = torch.rand(1, 3, 224, 288)
+    with torch.no_grad():
+        yo = ref(img)
+        yc = ours(img.to(DEV))
+    torch.cuda.synchronize()
+    assert yc.shape == yo.shape == (1, 1, 224, 288)
+    err = rel_l2(yc, yo)
+    _report("full model 224x288", {"depth": err})
+    assert err < TOL, err

@@ -1,0 +1,55 @@
+"""Host-side logic that needs no GPU: module tree / state_dict compatibility with the reference, constructor
+validation, the product path's refusal to run without CUDA."""
+import pytest
+import torch
+
+import monocular_depth_estimation_b200 as pkg
+from tests.helpers import load_golden
+
+
+def test_state_dict_keys_and_shapes_match_reference_checkpoint():
+    g = load_golden("layer_9x10_c64")
+    ref_sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    layer = pkg.BasicCRFLayer(dim=64, depth=2, num_heads=2, v_dim=64, window_size=7)
+    sd = layer.state_dict()
+    assert sorted(sd.keys()) == sorted(ref_sd.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref_sd[k].shape), k
+        assert str(v.dtype).split(".")[-1] == str(ref_sd[k].dtype), k
+    idx = sd["blocks.0.attn.relative_position_index"]
+    assert idx.dtype == torch.int64 and (idx.numpy() == ref_sd["blocks.0.attn.relative_position_index"]).all()
+    layer.load_state_dict({k: torch.from_numpy(v) for k, v in ref_sd.items()}, strict=True)
+
+
+def test_blocks_alternate_shift_and_scale():
+    layer = pkg.BasicCRFLayer(dim=128, depth=4, num_heads=4, v_dim=128)
+    assert [b.shift_size for b in layer.blocks] == [0, 3, 0, 3]
+    assert abs(layer.blocks[0].attn.scale - 32 ** -0.5) < 1e-12
+    assert len(layer.blocks[0].fused_params()) == 13
+
+
+def test_constructor_validation():
+    with pytest.raises(AssertionError, match="shift_size must in 0-window_size"):
+        pkg.CRFBlock(64, 2, 64, window_size=7, shift_size=9)
+    with pytest.raises(NotImplementedError):
+        pkg.CRFBlock(64, 2, 64, drop_path=0.1)
+    with pytest.raises(NotImplementedError):
+        pkg.WindowAttention(64, (7, 7), 2, 64, attn_drop=0.5)
+
+
+def test_no_cpu_fallback():
+    blk = pkg.CRFBlock(64, 2, 64)
+    blk.H, blk.W = 7, 7
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        blk(torch.randn(1, 49, 64), torch.randn(1, 7, 7, 64), None)
+
+
+def test_model_tree_matches_reference_prefixes():
+    from monocular_depth_estimation_b200.model import PTModel
+    m = PTModel()
+    keys = m.state_dict().keys()
+    assert "Unet.1.crf0.crf_layer.blocks.1.attn.qk.weight" in keys
+    assert "Unet.1.crf3.norm_crf.weight" in keys and "Unet.1.conv0.weight" in keys
+    assert "Unet.0.original_model.features.0.0.weight" in keys
+    n = sum(p.numel() for p in m.parameters())
+    assert abs(n / 1e6 - 45.07) < 3.0   # 45.07 M (encoder incl. the unused classifier here)
