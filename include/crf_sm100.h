@@ -143,7 +143,7 @@ enum {
   CRF_EPI_BIAS_RES_F32 = 2,/* out0 f32 = acc + bias + res(aux1 f32)                             */
   CRF_EPI_BIAS_GELU = 3,   /* out0 bf16 = pre = acc + bias (optional), out1 bf16 = gelu(pre)    */
   CRF_EPI_MUL_DGELU = 4,   /* out0 bf16 = acc * gelu'(pre), pre = aux1 bf16                     */
-  CRF_EPI_ATOMIC_F32 = 5   /* out0 f32 += acc (split-K weight gradients)                        */
+  CRF_EPI_SPLITK_F32 = 5   /* out0 f32 += acc; split-K partial tiles in `workspace` + reduce  */
 };
 
 /* D[M,N] = sum_k A(m,k) * B(n,k) on tcgen05 (bf16 operands, fp32 accumulate in TMEM), TMA-fed.
@@ -156,15 +156,19 @@ typedef struct crf_gemm_args {
   int32_t a_major, b_major;
   int32_t M, N, K;
   int32_t epilogue;
-  int32_t split_k;         /* >= 1; only with CRF_EPI_ATOMIC_F32 */
+  int32_t split_k;         /* CRF_EPI_SPLITK_F32 only: 0 = automatic, > 0 = upper bound on the K splits */
   void* out0; void* out1;
   const float* bias;       /* (N) or NULL */
   const void* aux1;        /* residual f32 (M,N) or pre bf16 (M,N) */
   int64_t ld_out;          /* row stride (elements) of out0/out1/aux1 */
   float scale; int32_t scale_cols;
   int32_t device;
+  void* workspace;         /* CRF_EPI_SPLITK_F32: fp32 partial tiles (crf_gemm_workspace_bytes) or NULL */
+  size_t workspace_bytes;
 } crf_gemm_args;
 int crf_gemm(const crf_gemm_args* a, void* stream);
+/* workspace a CRF_EPI_SPLITK_F32 GEMM of this shape wants (0 when it runs as a single split) */
+size_t crf_gemm_workspace_bytes(int M, int N, int K, int device);
 
 /* LayerNorm forward over channels with a layout change: x (B, T_img, C) with arbitrary strides ->
  * xn bf16 (T, C), stats f32 (T, 2) = (mean, rstd), optional contiguous f32 copy of x. */

@@ -20,12 +20,12 @@ EPI_STORE_BF16 = 1
 EPI_BIAS_RES_F32 = 2
 EPI_BIAS_GELU = 3
 EPI_MUL_DGELU = 4
-EPI_ATOMIC_F32 = 5
+EPI_SPLITK_F32 = 5
 
 # every symbol include/crf_sm100.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
     "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_timing_enable", "crf_timing_report", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
-    "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_ln_fwd", "crf_ln_bwd",
+    "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_gemm_workspace_bytes", "crf_ln_fwd", "crf_ln_bwd",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd",
 )
 
@@ -64,6 +64,7 @@ class GemmArgs(C.Structure):
         ("ld_out", C.c_int64),
         ("scale", C.c_float), ("scale_cols", C.c_int32),
         ("device", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -86,6 +87,8 @@ def _declare(lib):
     lib.crf_window_scatter.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_shift_mask.argtypes = [vp, i32, i32, i32, i32, vp]
     lib.crf_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.crf_gemm_workspace_bytes.restype = sz
+    lib.crf_gemm_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.crf_ln_fwd.argtypes = [vp, i32, i64, i64, i64, i32, i32, i32, vp, vp, f32, vp, vp, vp, i32, vp]
     lib.crf_ln_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.crf_colsum_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
@@ -93,7 +96,7 @@ def _declare(lib):
     lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp]
     lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
-        if name not in ("crf_last_error", "crf_kernel_launches", "crf_timing_report"):
+        if name not in ("crf_last_error", "crf_kernel_launches", "crf_timing_report", "crf_gemm_workspace_bytes"):
             getattr(lib, name).restype = i32
     lib.crf_kernel_launches.restype = C.c_longlong
     lib.crf_kernel_launches.argtypes = []

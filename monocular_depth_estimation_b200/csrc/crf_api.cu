@@ -14,7 +14,7 @@ struct SavedLayout {
 };
 // Layout of the backward workspace.
 struct BwdLayout {
-  size_t dyb, dhpre, dxn, dx1, dx1b, dob, dqk, total;
+  size_t dyb, dhpre, dxn, dx1, dx1b, dob, dqk, partials, partials_bytes, total;
 };
 
 bool x_is_plain(const crf_block_desc& d) {
@@ -62,6 +62,16 @@ BwdLayout bwd_layout(const crf_block_desc& d) {
   L.dx1b = take(T * C * 2);
   L.dob = take(T * C * 2);
   L.dqk = take(T * 2 * C * 2);
+  // split-K partial tiles of the four weight-gradient GEMMs (used one after the other)
+  const int Ti = static_cast<int>(T), Ci = d.C;
+  size_t pb = 0;
+  const int shapes[4][2] = {{Ci, 4 * Ci}, {4 * Ci, Ci}, {Ci, Ci}, {2 * Ci, Ci}};
+  for (auto& s : shapes) {
+    const size_t b = gemm_splitk_workspace_bytes(s[0], s[1], Ti, d.device, nullptr);
+    if (b > pb) pb = b;
+  }
+  L.partials_bytes = pb;
+  L.partials = take(pb);
   L.total = o;
   return L;
 }
@@ -77,16 +87,6 @@ int check_desc(const crf_block_desc* d) {
   CRF_CHECK(static_cast<int64_t>(d->B) * d->H * d->W * 4 * d->C < (int64_t(1) << 31) * 4,
             "problem too large for 32-bit token indexing");
   return 0;
-}
-
-int wgrad_splits(int M, int N, int K, int device) {
-  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
-  const int tiles = ((M + 127) / 128) * (N / BN);
-  const int chunks = (K + 63) / 64;
-  int s = (2 * num_sms(device) + tiles - 1) / tiles;
-  if (s > chunks) s = chunks;
-  if (s < 1) s = 1;
-  return s;
 }
 
 int gemm_fprop(const void* A, const void* W, int M, int N, int K, int epi, void* out0, void* out1, const float* bias,
@@ -108,11 +108,13 @@ int gemm_dgrad(const void* dY, const void* W, int M, int N, int K, int epi, void
   return launch_gemm(a, st);
 }
 // dW[M=Cout, N=Cin] += dY[T, Cout]^T * X[T, Cin]
-int gemm_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, int device, cudaStream_t st) {
+int gemm_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, void* ws, size_t ws_bytes, int device,
+               cudaStream_t st) {
   crf_gemm_args a{};
   a.A = dY; a.B = X; a.a_major = 1; a.b_major = 1;
-  a.M = M; a.N = N; a.K = K; a.epilogue = CRF_EPI_ATOMIC_F32; a.split_k = wgrad_splits(M, N, K, device);
+  a.M = M; a.N = N; a.K = K; a.epilogue = CRF_EPI_SPLITK_F32; a.split_k = 0;
   a.out0 = dW; a.ld_out = N; a.scale = 1.f; a.device = device;
+  a.workspace = ws; a.workspace_bytes = ws_bytes;
   return launch_gemm(a, st);
 }
 
@@ -230,23 +232,23 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
   // ---- MLP ----
   if (launch_cast_bf16(dy, Wk + W.dyb, static_cast<int64_t>(T) * C, st)) return 1;
   if (gemm_dgrad(Wk + W.dyb, S + L.wb_fc2, T, 4 * C, C, CRF_EPI_MUL_DGELU, Wk + W.dhpre, S + L.pre, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dyb, S + L.act, C, 4 * C, T, g->fc2_w, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dyb, S + L.act, C, 4 * C, T, g->fc2_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_colsum_bf16(Wk + W.dyb, g->fc2_b, T, C, st)) return 1;
   if (gemm_dgrad(Wk + W.dhpre, S + L.wb_fc1, T, C, 4 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_colsum_bf16(Wk + W.dhpre, g->fc1_b, T, 4 * C, st)) return 1;
   if (launch_ln_bwd(dxn, reinterpret_cast<const float*>(S + L.x1), reinterpret_cast<const float*>(S + L.stats2),
                     p->norm2_w, dy, dx1, Wk + W.dx1b, g->norm2_w, g->norm2_b, T, C, st))
     return 1;
   // ---- attention ----
   if (gemm_dgrad(Wk + W.dx1b, S + L.wb_proj, T, C, C, CRF_EPI_STORE_BF16, Wk + W.dob, nullptr, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_colsum_bf16(Wk + W.dx1b, g->proj_b, T, C, st)) return 1;
   if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, reinterpret_cast<const float*>(S + L.lse),
                       Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st))
     return 1;
   if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, dev, st)) return 1;
+  if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_colsum_bf16(Wk + W.dqk, g->qk_b, T, 2 * C, st)) return 1;
   if (launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, nullptr,
                     g->norm1_w, g->norm1_b, T, C, st))
@@ -272,8 +274,12 @@ int crf_shift_mask(float* mask, int H, int W, int window, int shift, void* strea
   return launch_shift_mask(mask, H, W, window, shift, static_cast<cudaStream_t>(stream));
 }
 
+size_t crf_gemm_workspace_bytes(int M, int N, int K, int device) {
+  return gemm_splitk_workspace_bytes(M, N, K, device, nullptr);
+}
+
 int crf_gemm(const crf_gemm_args* a, void* stream) {
-  CRF_CHECK(a && a->A && a->B && a->out0, "crf_gemm: null pointer");
+  CRF_CHECK(a && a->A && a->B && (a->out0 || a->out1), "crf_gemm: null pointer");
   DeviceGuard guard(a->device);
   CRF_CHECK(guard.ok, "cannot select device %d", a->device);
   return launch_gemm(*a, static_cast<cudaStream_t>(stream));

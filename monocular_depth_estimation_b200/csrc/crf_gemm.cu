@@ -13,6 +13,16 @@
 // issuer + TMEM allocator.  One 128 x BN output tile per CTA, K streamed in 64-element chunks through a
 // multi-stage mbarrier ring.  Two CTAs are co-resident per SM (<= 256 TMEM columns, <= ~100 KB smem each) so
 // one CTA's epilogue overlaps the other's main loop.
+//
+// Epilogue: these GEMMs are HBM-bound at the small-C decoder scales, so output and auxiliary traffic goes through
+// TMA as well.  The accumulator is drained in 128-byte-wide column slabs (64 bf16 or 32 fp32 columns): each thread
+// writes its row of the slab into a swizzled smem tile (conflict-free), one thread issues a TMA store of the
+// [128 x 128 B] box (rows beyond M are clipped by the tensor map), double-buffered.  Residual / pre-activation
+// tiles the epilogue needs are TMA-loaded into the same kind of slab one step ahead.  The slabs alias the
+// main-loop stages, which are dead once the accumulator barrier has fired.
+//
+// Split-K (weight gradients): each split stores its fp32 partial tile into a workspace [splits][Mpad][N] and a
+// second kernel reduces the partials into dW (+=): deterministic, and no per-element L2 atomics.
 #include "crf_host.h"
 #include "crf_ptx.cuh"
 
@@ -24,99 +34,48 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = BM * 128;  // 16 KB
+constexpr int kSlabBytes = BM * 128;   // 16 KB: 128 rows x 128 B
 
 struct EpiParams {
-  void* out0;
-  void* out1;
   const float* bias;
-  const void* aux1;
-  int64_t ld;
   float scale;
   int scale_cols;
+  int m_pad;       // split-K: rows per split in the partial buffer
+  int store_out0;  // BIAS_GELU: 0 -> skip the pre-activation output (inference)
 };
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int row, int n, const uint32_t (&r)[32]) {
-  float v[32];
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* bias, int n) {
+  if (bias == nullptr) return;
+  const float4* b4 = reinterpret_cast<const float4*>(bias + n);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  const int64_t off = static_cast<int64_t>(row) * ep.ld + n;
-
-  if constexpr (EPI == CRF_EPI_ATOMIC_F32) {
-    float* o = reinterpret_cast<float*>(ep.out0) + off;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
-    return;
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
   }
-
-  if (ep.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n);
+}
+// 32 fp32 values -> 4 x 16-byte chunks of bf16 at chunk index c0.. of row r of a swizzled slab
+__device__ __forceinline__ void store_bf16_32(uint8_t* slab, int r, int c0, const float (&v)[32]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-    }
-  }
-
-  if constexpr (EPI == CRF_EPI_STORE_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + off);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else if constexpr (EPI == CRF_EPI_STORE_BF16) {
-    if (n < ep.scale_cols) {  // scale_cols is a multiple of 32, so the whole chunk is on one side
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
-    }
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out0) + off);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-  } else if constexpr (EPI == CRF_EPI_BIAS_RES_F32) {
-    const float4* res = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux1) + off);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + off);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 q = __ldg(res + j);
-      o[j] = make_float4(v[4 * j] + q.x, v[4 * j + 1] + q.y, v[4 * j + 2] + q.z, v[4 * j + 3] + q.w);
-    }
-  } else if constexpr (EPI == CRF_EPI_BIAS_GELU) {
-    if (ep.out0 != nullptr) {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out0) + off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    uint4* o1 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out1) + off);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o1[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-  } else if constexpr (EPI == CRF_EPI_MUL_DGELU) {
-    const uint4* pre = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.aux1) + off);
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out0) + off);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 p = __ldg(pre + j);
-      const float g0 = v[8 * j + 0] * dgelu_erf(bf16_lo(p.x)), g1 = v[8 * j + 1] * dgelu_erf(bf16_hi(p.x));
-      const float g2 = v[8 * j + 2] * dgelu_erf(bf16_lo(p.y)), g3 = v[8 * j + 3] * dgelu_erf(bf16_hi(p.y));
-      const float g4 = v[8 * j + 4] * dgelu_erf(bf16_lo(p.z)), g5 = v[8 * j + 5] * dgelu_erf(bf16_hi(p.z));
-      const float g6 = v[8 * j + 6] * dgelu_erf(bf16_lo(p.w)), g7 = v[8 * j + 7] * dgelu_erf(bf16_hi(p.w));
-      o[j] = make_uint4(pack_bf16(g0, g1), pack_bf16(g2, g3), pack_bf16(g4, g5), pack_bf16(g6, g7));
-    }
-  }
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(slab + sw128_offset(r, c0 + j)) =
+        make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-            int total_chunks, int chunks_per_split, int stages, int a_major, int b_major, EpiParams ep) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+            const __grid_constant__ CUtensorMap tmAux, int M, int N, int total_chunks, int chunks_per_split, int stages,
+            int a_major, int b_major, EpiParams ep) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = kATileBytes + kBTileBytes;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr bool kOutF32 = (EPI == CRF_EPI_STORE_F32 || EPI == CRF_EPI_BIAS_RES_F32 || EPI == CRF_EPI_SPLITK_F32);
+  constexpr bool kHasAux = (EPI == CRF_EPI_BIAS_RES_F32 || EPI == CRF_EPI_MUL_DGELU);
+  constexpr bool kHasOut1 = (EPI == CRF_EPI_BIAS_GELU);
+  constexpr int kSlabCols = kOutF32 ? 32 : 64;
+  constexpr int kNumSlabs = BN / kSlabCols;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,22 +89,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + stages * kStageBytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  // barriers live after the stage ring: full[stages], empty[stages], tmem_full, aux[2], tmem_ptr
+  const uint32_t ring_bytes = static_cast<uint32_t>(stages) * kStageBytes < 4u * kSlabBytes
+                                  ? 4u * kSlabBytes
+                                  : static_cast<uint32_t>(stages) * kStageBytes;
+  const uint32_t bar_base = smem_base + ring_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * stages);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * stages + 1);
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + stages * kStageBytes + 8 * (2 * stages + 1));
+  auto aux_bar = [&](int s) { return bar_base + 8u * (2 * stages + 1 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * stages + 3);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + ring_bytes + 8 * (2 * stages + 3));
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO0);
+    if (kHasOut1) tma_prefetch_desc(&tmO1);
+    if (kHasAux) tma_prefetch_desc(&tmAux);
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(aux_bar(0), 1);
+    mbar_init(aux_bar(1), 1);
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -201,22 +169,96 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
+      umma_commit(tmem_full_bar);  // accumulator complete (and every smem stage is dead from here on)
     }
   } else {
-    // ===== epilogue: thread = accumulator row =====
+    // ===== epilogue: thread = accumulator row; slabs staged in smem, moved by TMA =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int row = m0 + threadIdx.x;
-    const bool row_ok = row < M;
+    const int r = threadIdx.x;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c, r);
-      tmem_ld_wait();
-      if (row_ok) epilogue_chunk<EPI>(ep, row, n0 + c, r);
+    // slab buffers (alias the dead main-loop stages): out0 [2] | out1-or-aux [2]
+    const uint32_t out0_s = smem_base, x_s = smem_base + 2 * kSlabBytes;
+    uint8_t* out0_g = smem_gen;
+    uint8_t* x_g = smem_gen + 2 * kSlabBytes;
+    const int out_row0 = (EPI == CRF_EPI_SPLITK_F32) ? static_cast<int>(blockIdx.z) * ep.m_pad + m0 : m0;
+
+    if (kHasAux && r == 0) {
+      mbar_expect_tx(aux_bar(0), kSlabBytes);
+      tma_load_2d(x_s, &tmAux, aux_bar(0), n0, m0);
     }
+#pragma unroll 1
+    for (int s = 0; s < kNumSlabs; ++s) {
+      const int buf = s & 1;
+      const int nc = n0 + s * kSlabCols;
+      if (r == 0) bulk_wait_read<1>();  // the store issued two slabs ago has drained buffer `buf`
+      named_bar_sync(1, 128);
+      if (kHasAux) {
+        if (r == 0 && s + 1 < kNumSlabs) {
+          mbar_expect_tx(aux_bar(buf ^ 1), kSlabBytes);
+          tma_load_2d(x_s + (buf ^ 1) * kSlabBytes, &tmAux, aux_bar(buf ^ 1), nc + kSlabCols, m0);
+        }
+        mbar_wait(aux_bar(buf), (s >> 1) & 1);
+      }
+      uint8_t* o0 = out0_g + buf * kSlabBytes;
+      uint8_t* xb = x_g + buf * kSlabBytes;
+#pragma unroll
+      for (int half = 0; half < kSlabCols / 32; ++half) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + s * kSlabCols + half * 32, acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        const int n = nc + half * 32;
+        if constexpr (EPI == CRF_EPI_STORE_F32 || EPI == CRF_EPI_SPLITK_F32) {
+          add_bias32(v, ep.bias, n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(o0 + sw128_offset(r, j)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if constexpr (EPI == CRF_EPI_BIAS_RES_F32) {
+          add_bias32(v, ep.bias, n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(xb + sw128_offset(r, j));
+            *reinterpret_cast<float4*>(o0 + sw128_offset(r, j)) =
+                make_float4(v[4 * j] + q.x, v[4 * j + 1] + q.y, v[4 * j + 2] + q.z, v[4 * j + 3] + q.w);
+          }
+        } else if constexpr (EPI == CRF_EPI_STORE_BF16) {
+          add_bias32(v, ep.bias, n);
+          if (n < ep.scale_cols) {  // scale_cols is a multiple of 32: a 32-column group is on one side
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
+          }
+          store_bf16_32(o0, r, half * 4, v);
+        } else if constexpr (EPI == CRF_EPI_BIAS_GELU) {
+          add_bias32(v, ep.bias, n);
+          if (ep.store_out0) store_bf16_32(o0, r, half * 4, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          store_bf16_32(xb, r, half * 4, v);
+        } else if constexpr (EPI == CRF_EPI_MUL_DGELU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 p = *reinterpret_cast<const uint4*>(xb + sw128_offset(r, half * 4 + j));
+            v[8 * j + 0] *= dgelu_erf(bf16_lo(p.x)); v[8 * j + 1] *= dgelu_erf(bf16_hi(p.x));
+            v[8 * j + 2] *= dgelu_erf(bf16_lo(p.y)); v[8 * j + 3] *= dgelu_erf(bf16_hi(p.y));
+            v[8 * j + 4] *= dgelu_erf(bf16_lo(p.z)); v[8 * j + 5] *= dgelu_erf(bf16_hi(p.z));
+            v[8 * j + 6] *= dgelu_erf(bf16_lo(p.w)); v[8 * j + 7] *= dgelu_erf(bf16_hi(p.w));
+          }
+          store_bf16_32(o0, r, half * 4, v);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (r == 0) {
+        if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s + buf * kSlabBytes, nc, out_row0);
+        if (kHasOut1) tma_store_2d(&tmO1, x_s + buf * kSlabBytes, nc, out_row0);
+        bulk_commit();
+      }
+    }
+    if (r == 0) bulk_wait_read<0>();
   }
 
   tc_fence_before();
@@ -227,18 +269,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// dW[m,n] += sum_z part[z][m][n]
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int M, int N, int m_pad, int splits) {
+  const int64_t i4 = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t total4 = static_cast<int64_t>(M) * N / 4;
+  if (i4 >= total4) return;
+  const int64_t e = i4 * 4;
+  const int m = static_cast<int>(e / N), n = static_cast<int>(e - static_cast<int64_t>(m) * N);
+  float4 acc = *reinterpret_cast<const float4*>(out + e);
+  const float* p = part + static_cast<int64_t>(m) * N + n;
+  const int64_t zs = static_cast<int64_t>(m_pad) * N;
+#pragma unroll 4
+  for (int z = 0; z < splits; ++z) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + z * zs));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + e) = acc;
+}
+
+struct Launch {
+  CUtensorMap tmA, tmB, tmO0, tmO1, tmAux;
+  int total_chunks, cps, splits, m_pad;
+};
+
 template <int BN, int EPI>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const crf_gemm_args& a, int total_chunks,
-               int chunks_per_split, int splits, cudaStream_t st) {
+int launch_one(const Launch& L, const crf_gemm_args& a, cudaStream_t st) {
   constexpr int kStageBytes = kATileBytes + BN * 128;
   // 2 co-resident CTAs/SM when K is short; one deep ring when K is long.
-  int stages = (total_chunks / splits >= 8) ? (BN == 256 ? 4 : 6) : (BN == 256 ? 2 : 3);
-  if (stages > chunks_per_split) stages = chunks_per_split < 2 ? 2 : chunks_per_split;
-  const size_t smem = static_cast<size_t>(stages) * kStageBytes + 1024 + 8 * (2 * stages + 2);
+  int stages = (L.cps >= 8) ? (BN == 256 ? 4 : 6) : (BN == 256 ? 2 : 3);
+  if (stages > L.cps) stages = L.cps < 2 ? 2 : L.cps;
+  size_t ring = static_cast<size_t>(stages) * kStageBytes;
+  if (ring < 4u * kSlabBytes) ring = 4u * kSlabBytes;
+  const size_t smem = ring + 1024 + 8 * (2 * stages + 4);
   auto kern = gemm_kernel<BN, EPI>;
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  EpiParams ep{a.out0, a.out1, a.bias, a.aux1, a.ld_out, a.scale, a.scale_cols};
-  dim3 grid((a.M + BM - 1) / BM, a.N / BN, splits);
+  EpiParams ep{a.bias, a.scale, a.scale_cols, L.m_pad, a.out0 != nullptr ? 1 : 0};
+  dim3 grid((a.M + BM - 1) / BM, a.N / BN, L.splits);
   const double mn = static_cast<double>(a.M) * a.N;
   const double out_bytes = EPI == CRF_EPI_STORE_BF16 ? 2 * mn
                            : EPI == CRF_EPI_BIAS_RES_F32 ? 8 * mn
@@ -246,28 +313,49 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const crf_gemm_ar
                            : 4 * mn;
   KernelTimer tm(st, 2.0 * mn * a.K, 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
                  "gemm_%s_epi%d_M%d_N%d_K%d", a.a_major ? "wgrad" : (a.b_major ? "dgrad" : "fprop"), EPI, a.M, a.N, a.K);
-  kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a.M, a.N, total_chunks, chunks_per_split, stages, a.a_major,
-                                     a.b_major, ep);
+  kern<<<grid, kThreads, smem, st>>>(L.tmA, L.tmB, L.tmO0, L.tmO1, L.tmAux, a.M, a.N, L.total_chunks, L.cps, stages,
+                                     a.a_major, a.b_major, ep);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;
 }
 
 template <int BN>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const crf_gemm_args& a, int tc, int cps, int splits,
-              cudaStream_t st) {
-  switch (a.epilogue) {
-    case CRF_EPI_STORE_F32: return launch_one<BN, CRF_EPI_STORE_F32>(tmA, tmB, a, tc, cps, splits, st);
-    case CRF_EPI_STORE_BF16: return launch_one<BN, CRF_EPI_STORE_BF16>(tmA, tmB, a, tc, cps, splits, st);
-    case CRF_EPI_BIAS_RES_F32: return launch_one<BN, CRF_EPI_BIAS_RES_F32>(tmA, tmB, a, tc, cps, splits, st);
-    case CRF_EPI_BIAS_GELU: return launch_one<BN, CRF_EPI_BIAS_GELU>(tmA, tmB, a, tc, cps, splits, st);
-    case CRF_EPI_MUL_DGELU: return launch_one<BN, CRF_EPI_MUL_DGELU>(tmA, tmB, a, tc, cps, splits, st);
-    case CRF_EPI_ATOMIC_F32: return launch_one<BN, CRF_EPI_ATOMIC_F32>(tmA, tmB, a, tc, cps, splits, st);
-    default: return set_error("crf_gemm: unknown epilogue %d", a.epilogue);
+int launch_bn(const Launch& L, const crf_gemm_args& a, int epi, cudaStream_t st) {
+  switch (epi) {
+    case CRF_EPI_STORE_F32: return launch_one<BN, CRF_EPI_STORE_F32>(L, a, st);
+    case CRF_EPI_STORE_BF16: return launch_one<BN, CRF_EPI_STORE_BF16>(L, a, st);
+    case CRF_EPI_BIAS_RES_F32: return launch_one<BN, CRF_EPI_BIAS_RES_F32>(L, a, st);
+    case CRF_EPI_BIAS_GELU: return launch_one<BN, CRF_EPI_BIAS_GELU>(L, a, st);
+    case CRF_EPI_MUL_DGELU: return launch_one<BN, CRF_EPI_MUL_DGELU>(L, a, st);
+    case CRF_EPI_SPLITK_F32: return launch_one<BN, CRF_EPI_SPLITK_F32>(L, a, st);
+    default: return set_error("crf_gemm: unknown epilogue %d", epi);
+  }
+}
+
+int launch_bn_dispatch(int BN, const Launch& L, const crf_gemm_args& a, int epi, cudaStream_t st) {
+  switch (BN) {
+    case 256: return launch_bn<256>(L, a, epi, st);
+    case 128: return launch_bn<128>(L, a, epi, st);
+    default: return launch_bn<64>(L, a, epi, st);
   }
 }
 
 }  // namespace
+
+// Number of K splits a weight-gradient GEMM will use and the fp32 partial-tile workspace it needs.
+size_t gemm_splitk_workspace_bytes(int M, int N, int K, int device, int* splits_out) {
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int chunks = (K + BK - 1) / BK;
+  int s = num_sms(device) / tiles;  // about one CTA per SM, each with a deep pipeline over its token range
+  if (s > chunks) s = chunks;
+  if (s < 1) s = 1;
+  if (splits_out) *splits_out = s;
+  if (s == 1) return 0;
+  const size_t m_pad = static_cast<size_t>((M + BM - 1) / BM) * BM;
+  return static_cast<size_t>(s) * m_pad * N * sizeof(float);
+}
 
 int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   CRF_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "crf_gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
@@ -276,30 +364,81 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   CRF_CHECK(a.b_major == 0 || a.b_major == 1, "crf_gemm: bad b_major");
   CRF_CHECK(a.a_major == 1 || a.K % 8 == 0, "crf_gemm: K-major A needs K %% 8 == 0 (K=%d)", a.K);
   CRF_CHECK(a.a_major == 0 || a.M % 8 == 0, "crf_gemm: MN-major A needs M %% 8 == 0 (M=%d)", a.M);
-  CRF_CHECK(a.split_k >= 1, "crf_gemm: split_k must be >= 1");
-  CRF_CHECK(a.split_k == 1 || a.epilogue == CRF_EPI_ATOMIC_F32, "crf_gemm: split_k needs the atomic epilogue");
+  CRF_CHECK(a.ld_out == a.N, "crf_gemm: outputs must be dense (ld_out == N)");
   const int BN = (a.N % 256 == 0) ? 256 : (a.N % 128 == 0 ? 128 : 64);
 
-  CUtensorMap tmA, tmB;
+  Launch L{};
   if (a.a_major == 0) {
-    if (make_tmap_bf16(&tmA, a.A, a.M, a.K, BM)) return 1;
+    if (make_tmap_bf16(&L.tmA, a.A, a.M, a.K, BM)) return 1;
   } else {
-    if (make_tmap_bf16(&tmA, a.A, a.K, a.M, 64)) return 1;
+    if (make_tmap_bf16(&L.tmA, a.A, a.K, a.M, 64)) return 1;
   }
   if (a.b_major == 0) {
-    if (make_tmap_bf16(&tmB, a.B, a.N, a.K, BN)) return 1;
+    if (make_tmap_bf16(&L.tmB, a.B, a.N, a.K, BN)) return 1;
   } else {
-    if (make_tmap_bf16(&tmB, a.B, a.K, a.N, 64)) return 1;
+    if (make_tmap_bf16(&L.tmB, a.B, a.K, a.N, 64)) return 1;
   }
-  const int total_chunks = (a.K + BK - 1) / BK;
-  int splits = a.split_k > total_chunks ? total_chunks : a.split_k;
-  int cps = (total_chunks + splits - 1) / splits;
-  splits = (total_chunks + cps - 1) / cps;  // no empty split
-  switch (BN) {
-    case 256: return launch_bn<256>(tmA, tmB, a, total_chunks, cps, splits, st);
-    case 128: return launch_bn<128>(tmA, tmB, a, total_chunks, cps, splits, st);
-    default: return launch_bn<64>(tmA, tmB, a, total_chunks, cps, splits, st);
+  L.total_chunks = (a.K + BK - 1) / BK;
+  L.splits = 1;
+  L.cps = L.total_chunks;
+  L.m_pad = (a.M + BM - 1) / BM * BM;
+  L.tmO1 = L.tmA;  // placeholders for unused maps (never dereferenced by the kernel)
+  L.tmAux = L.tmA;
+  int epi = a.epilogue;
+
+  if (epi == CRF_EPI_SPLITK_F32) {
+    // out0 (M,N) f32 += A^T B.  One split: in-place accumulate (residual = out0).  Otherwise partials + reduce.
+    CRF_CHECK(a.out0 != nullptr, "crf_gemm: out0 is null");
+    int splits = 1;
+    gemm_splitk_workspace_bytes(a.M, a.N, a.K, a.device, &splits);
+    if (a.split_k > 0 && a.split_k < splits) splits = a.split_k;
+    const size_t per_split = static_cast<size_t>(L.m_pad) * a.N * sizeof(float);
+    if (splits > 1) {
+      const size_t fit = a.workspace == nullptr ? 0 : a.workspace_bytes / per_split;
+      if (fit < static_cast<size_t>(splits)) splits = fit < 1 ? 1 : static_cast<int>(fit);
+    }
+    crf_gemm_args b = a;
+    b.bias = nullptr;
+    if (splits <= 1) {
+      if (make_tmap_f32(&L.tmO0, a.out0, a.M, a.N, BM)) return 1;
+      L.tmAux = L.tmO0;
+      return launch_bn_dispatch(BN, L, b, CRF_EPI_BIAS_RES_F32, st);
+    }
+    L.cps = (L.total_chunks + splits - 1) / splits;
+    L.splits = (L.total_chunks + L.cps - 1) / L.cps;  // no empty split
+    if (make_tmap_f32(&L.tmO0, a.workspace, static_cast<uint64_t>(L.splits) * L.m_pad, a.N, BM)) return 1;
+    if (launch_bn_dispatch(BN, L, b, epi, st)) return 1;
+    const int64_t total4 = static_cast<int64_t>(a.M) * a.N / 4;
+    KernelTimer tm(st, 0.0, 4.0 * a.M * a.N * (L.splits + 2), "splitk_reduce_M%d_N%d_S%d", a.M, a.N, L.splits);
+    splitk_reduce_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float*>(a.workspace), reinterpret_cast<float*>(a.out0), a.M, a.N, L.m_pad, L.splits);
+    CRF_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
   }
+
+  const bool out_f32 = (epi == CRF_EPI_STORE_F32 || epi == CRF_EPI_BIAS_RES_F32);
+  if (epi == CRF_EPI_BIAS_GELU) {
+    CRF_CHECK(a.out1 != nullptr, "crf_gemm: BIAS_GELU needs out1");
+    if (a.out0 != nullptr) {
+      if (make_tmap_bf16(&L.tmO0, a.out0, a.M, a.N, BM)) return 1;
+    } else {
+      L.tmO0 = L.tmA;
+    }
+    if (make_tmap_bf16(&L.tmO1, a.out1, a.M, a.N, BM)) return 1;
+  } else {
+    CRF_CHECK(a.out0 != nullptr, "crf_gemm: out0 is null");
+    if (out_f32 ? make_tmap_f32(&L.tmO0, a.out0, a.M, a.N, BM) : make_tmap_bf16(&L.tmO0, a.out0, a.M, a.N, BM))
+      return 1;
+  }
+  if (epi == CRF_EPI_BIAS_RES_F32) {
+    CRF_CHECK(a.aux1 != nullptr, "crf_gemm: BIAS_RES_F32 needs aux1 (residual)");
+    if (make_tmap_f32(&L.tmAux, a.aux1, a.M, a.N, BM)) return 1;
+  } else if (epi == CRF_EPI_MUL_DGELU) {
+    CRF_CHECK(a.aux1 != nullptr, "crf_gemm: MUL_DGELU needs aux1 (pre-activation)");
+    if (make_tmap_bf16(&L.tmAux, a.aux1, a.M, a.N, BM)) return 1;
+  }
+  return launch_bn_dispatch(BN, L, a, epi, st);
 }
 
 }  // namespace crf

@@ -40,6 +40,24 @@ void load_encode() {
 }
 }  // namespace
 
+int make_tmap_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  std::call_once(g_encode_once, load_encode);
+  CRF_CHECK(g_encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  CRF_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: base pointer %p is not 16-byte aligned", ptr);
+  CRF_CHECK(cols % 4 == 0, "TMA: row pitch must be a multiple of 16 bytes (cols=%llu)", (unsigned long long)cols);
+  CRF_CHECK(box_rows >= 1 && box_rows <= 256, "TMA: box rows %u out of range", box_rows);
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * 4};
+  const cuuint32_t box[2] = {32, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CRF_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed: %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
+            (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return 0;
+}
+
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   std::call_once(g_encode_once, load_encode);
   CRF_CHECK(g_encode != nullptr, "cuTensorMapEncodeTiled is not available from the driver");

@@ -44,6 +44,8 @@ struct DeviceGuard {
 
 // 2-D bf16 row-major tensor (rows, cols) -> tiled tensor map with 128-byte swizzle, box = (64 cols, box_rows).
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// 2-D fp32 row-major tensor (rows, cols) -> box = (32 cols, box_rows), 128-byte swizzle (epilogue tiles).
+int make_tmap_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 int num_sms(int device);
 void note_launch(int n = 1);
@@ -67,6 +69,7 @@ long long launch_count();
 
 // ---- internal launchers (stream-ordered, no allocation) ----
 int launch_gemm(const crf_gemm_args& a, cudaStream_t st);
+size_t gemm_splitk_workspace_bytes(int M, int N, int K, int device, int* splits_out);
 int launch_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
                   const float* gamma, const float* beta, float eps, void* xn, float* stats, float* x_copy,
                   cudaStream_t st);

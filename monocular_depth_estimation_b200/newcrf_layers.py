@@ -178,4 +178,7 @@ class NewCRF(nn.Module):
         v_hwc = v.permute(0, 2, 3, 1)              # (B, H, W, C) view of NCHW
         y = self.crf_layer(tokens, v_hwc, Wh, Ww)[0]
         y = self.norm_crf(y)
-        return y.view(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2).contiguous()
+        out = y.view(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2)
+        if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+            return out  # channels-last pipeline: the token-major result already IS NHWC memory, no copy needed
+        return out.contiguous()

@@ -50,7 +50,7 @@ def _rand_bf16(*shape, seed=0, scale=1.0):
 # ---------------------------------------------------------------------------------------------------------
 # GEMM: the three operand orientations
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 128), (1000, 256, 512), (257, 64, 192),
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (90, 128, 128), (300, 128, 128), (1000, 256, 512), (257, 64, 192),
                                    (4800, 512, 128), (640, 1024, 256), (384, 128, 2048), (200, 256, 4096)])
 def test_gemm_fprop(M, N, K):
     ops, L = _ops(), _L()
@@ -74,15 +74,16 @@ def test_gemm_dgrad(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,split", [(128, 64, 64, 1), (128, 128, 1000, 1), (512, 128, 1000, 4),
-                                         (64, 256, 333, 3), (256, 512, 4800, 16), (1024, 256, 2400, 8)])
+                                         (64, 256, 333, 3), (256, 512, 4800, 16), (1024, 256, 2400, 0),
+                                         (128, 512, 153600, 0), (4096, 1024, 2400, 0), (2048, 512, 9600, 0)])
 def test_gemm_wgrad(M, N, K, split):
-    """dW (M,N) += dY (K,M)^T @ X (K,N): both operands MN-major, split-K over tokens with fp32 atomics."""
+    """dW (M,N) += dY (K,M)^T @ X (K,N): both operands MN-major, split-K over tokens (partials + reduce)."""
     ops, L = _ops(), _L()
     A, B = _rand_bf16(K, M, seed=5), _rand_bf16(K, N, seed=6, scale=K ** -0.5)
-    out = torch.zeros(M, N, device=DEV)
-    ops.gemm(A, B, M, N, K, a_major=1, b_major=1, epilogue=L.EPI_ATOMIC_F32, out0=out, split_k=split)
+    out = torch.ones(M, N, device=DEV)        # accumulate semantics: starts non-zero
+    ops.gemm(A, B, M, N, K, a_major=1, b_major=1, epilogue=L.EPI_SPLITK_F32, out0=out, split_k=split)
     torch.cuda.synchronize()
-    _check(out, A.float().t() @ B.float(), 1e-5, f"wgrad {M}x{N}x{K} split {split}")
+    _check(out - 1.0, A.float().t() @ B.float(), 2e-5, f"wgrad {M}x{N}x{K} split {split}")
 
 
 def test_gemm_epilogues():
