@@ -17,74 +17,15 @@
 //   dP = dO * [V_A;V_B]^T   dV = Pbd^T * dO   dK = dSbd^T * Q   dQ = dSbd * [K_A;K_B]
 // The relative-position-bias gradient is accumulated in registers across all pairs a CTA processes (each thread
 // owns one query row) and flushed once per CTA.
-#include "crf_host.h"
-#include "crf_ptx.cuh"
-#include "crf_window.cuh"
+#include <stdlib.h>
+
+#include "crf_attn_common.cuh"
 
 namespace crf {
 
 namespace {
 
 constexpr int kAttnThreads = 160;  // warps 0-3: one thread per tile row; warp 4: MMA issuer / TMEM owner
-constexpr int kNTok = 49;
-
-struct AttnParams {
-  WindowGeom gm;
-  int B, C, nH;
-  int total_windows;  // B * nW
-  int npairs;
-  const __nv_bfloat16* qk;   // (T, 2C)
-  const __nv_bfloat16* vb;   // (T, C)
-  const float* qk_bias;      // (2C)
-  const float* table;        // (169, nH)
-  float scale;
-  // forward
-  __nv_bfloat16* o;          // (T, C)
-  float* lse;                // (B*nW, nH, 64)
-  // backward
-  const __nv_bfloat16* dout; // (T, C)
-  __nv_bfloat16* dqk;        // (T, 2C)
-  float* dv;                 // (T, C)
-  int dv_acc;
-  float* d_table;            // (169, nH)
-  float* d_qk_bias;          // (2C)
-};
-
-// Token index of tile row r of a window pair: >= 0 real token, -1 zero-pad token, -2 dead row.
-__device__ __forceinline__ int row_token(const AttnParams& P, int pair, int r, int& window_global, int& pos) {
-  const int half = r >> 6;
-  pos = r & 63;
-  window_global = 2 * pair + half;
-  if (pos >= kNTok || window_global >= P.total_windows) return -2;
-  const int b = window_global / P.gm.nW;
-  const int win = window_global - b * P.gm.nW;
-  const int src = P.gm.source(win, pos);
-  return src < 0 ? -1 : b * P.gm.H * P.gm.W + src;
-}
-
-// copy one 64-byte head slice (32 bf16) of a token row into row r of a SW64 tile
-__device__ __forceinline__ void gather_row64(uint32_t tile, int r, const __nv_bfloat16* src) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) cp_async16(tile + sw64_offset(r, c), src + 8 * c);
-}
-__device__ __forceinline__ void zero_row64(uint8_t* tile_gen, int r) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(tile_gen + sw64_offset(r, c)) = make_uint4(0, 0, 0, 0);
-}
-__device__ __forceinline__ void bias_row64(uint8_t* tile_gen, int r, const float* bias32) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(bias32 + 8 * c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias32 + 8 * c + 4));
-    *reinterpret_cast<uint4*>(tile_gen + sw64_offset(r, c)) =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-  }
-}
-
-// relative_position_index[i][j] = (yi - yj + 6) * 13 + (xi - xj + 6)   (newcrf_layers.py:90-99)
-__device__ __forceinline__ int rpb_base(int pos) { return (pos / 7) * 13 + (pos % 7) + 84; }
-__host__ __device__ constexpr int rpb_col(int j) { return (j / 7) * 13 + (j % 7); }
-
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -514,26 +455,19 @@ attn_bwd_kernel(const AttnParams P) {
   }
 }
 
-int fill_params(AttnParams& P, const crf_block_desc& d) {
-  CRF_CHECK(d.C % d.num_heads == 0 && d.C / d.num_heads == 32,
-            "attention core: head_dim must be 32 (C=%d, heads=%d)", d.C, d.num_heads);
-  CRF_CHECK(d.window == 7, "attention core: window must be 7 (got %d)", d.window);
-  CRF_CHECK(d.shift >= 0 && d.shift < d.window, "shift_size must in 0-window_size");
-  P.gm = WindowGeom(d.H, d.W, d.window, d.shift);
-  P.B = d.B;
-  P.C = d.C;
-  P.nH = d.num_heads;
-  P.total_windows = d.B * P.gm.nW;
-  P.npairs = (P.total_windows + 1) / 2;
-  return 0;
-}
-
 }  // namespace
+
+int launch_attn_fwd_pipe(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
+int launch_attn_bwd_pipe(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
+static bool use_legacy_attn() {
+  static const bool v = getenv("CRF_ATTN_LEGACY") != nullptr;  // development switch: single-buffer kernels
+  return v;
+}
 
 int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
                     const float* table, void* o, float* lse, cudaStream_t st) {
   AttnParams P{};
-  if (fill_params(P, d)) return 1;
+  if (fill_attn_params(P, d)) return 1;
   P.qk = reinterpret_cast<const __nv_bfloat16*>(qk);
   P.vb = reinterpret_cast<const __nv_bfloat16*>(vb);
   P.qk_bias = qk_bias;
@@ -541,6 +475,7 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.scale = scale;
   P.o = reinterpret_cast<__nv_bfloat16*>(o);
   P.lse = lse;
+  if (!use_legacy_attn()) return launch_attn_fwd_pipe(P, d, st);
   const size_t smem = 40960 + 176 * 4 + 128 + 32 + 1024;
   CRF_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int gx = (num_sms(d.device) * 4 + P.nH - 1) / P.nH;
@@ -559,7 +494,7 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
                     const float* table, const float* lse, const void* dout, void* dqk, float* dv, int dv_acc,
                     float* d_table, float* d_qk_bias, cudaStream_t st) {
   AttnParams P{};
-  if (fill_params(P, d)) return 1;
+  if (fill_attn_params(P, d)) return 1;
   P.qk = reinterpret_cast<const __nv_bfloat16*>(qk);
   P.vb = reinterpret_cast<const __nv_bfloat16*>(vb);
   P.qk_bias = qk_bias;
@@ -572,6 +507,7 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.dv_acc = dv_acc;
   P.d_table = d_table;
   P.d_qk_bias = d_qk_bias;
+  if (!use_legacy_attn()) return launch_attn_bwd_pipe(P, d, st);
   const size_t smem = 98304 + 176 * 4 + 128 + 32 + 1024;
   CRF_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int gx = (num_sms(d.device) * 2 + P.nH - 1) / P.nH;

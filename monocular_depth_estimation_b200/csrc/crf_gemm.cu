@@ -9,8 +9,9 @@
 // written by a TMA box (64 cols x R rows).  A K-major operand uses one box of R = tile rows; an MN-major
 // operand uses (tile MN extent / 64) boxes of 64 K-rows each, 8 KB apart (the descriptor's leading byte offset).
 //
-// CTA = 6 warps: warps 0-3 epilogue (thread = accumulator row = TMEM lane), warp 4 TMA producer, warp 5 MMA
-// issuer + TMEM allocator.  One 128 x BN output tile per CTA, K streamed in 64-element chunks through a
+// CTA = 10 warps: warps 0-7 epilogue (two groups of four; thread = accumulator row = TMEM lane; the groups take
+// alternate column slabs, which doubles the warps available to hide the GELU / conversion latency), warp 8 TMA
+// producer, warp 9 MMA issuer + TMEM allocator.  One 128 x BN output tile per CTA, K streamed in 64-element chunks through a
 // multi-stage mbarrier ring.  Two CTAs are co-resident per SM (<= 256 TMEM columns, <= ~100 KB smem each) so
 // one CTA's epilogue overlaps the other's main loop.
 //
@@ -32,7 +33,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // 8 epilogue warps (two groups of 4), 1 TMA warp, 1 MMA warp
 constexpr int kATileBytes = BM * 128;  // 16 KB
 constexpr int kSlabBytes = BM * 128;   // 16 KB: 128 rows x 128 B
 
@@ -101,7 +102,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * stages + 3);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + ring_bytes + 8 * (2 * stages + 3));
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO0);
@@ -116,7 +117,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_init(aux_bar(1), 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_ptr_addr, kTmemCols);
     tmem_relinquish();
   }
@@ -125,7 +126,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int i = 0; i < nk; ++i) {
@@ -149,7 +150,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(1u, static_cast<uint32_t>(a_major), static_cast<uint32_t>(b_major), BM, BN);
@@ -173,33 +174,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===== epilogue: thread = accumulator row; slabs staged in smem, moved by TMA =====
+    // Group e (warps 4e..4e+3) drains slabs e, e+2, ...; each group owns one output slab and one aux/out1 slab.
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int r = threadIdx.x;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    // slab buffers (alias the dead main-loop stages): out0 [2] | out1-or-aux [2]
+    const int e = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const int buf = e;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t out0_s = smem_base, x_s = smem_base + 2 * kSlabBytes;
     uint8_t* out0_g = smem_gen;
     uint8_t* x_g = smem_gen + 2 * kSlabBytes;
     const int out_row0 = (EPI == CRF_EPI_SPLITK_F32) ? static_cast<int>(blockIdx.z) * ep.m_pad + m0 : m0;
 
-    if (kHasAux && r == 0) {
-      mbar_expect_tx(aux_bar(0), kSlabBytes);
-      tma_load_2d(x_s, &tmAux, aux_bar(0), n0, m0);
+    if (kHasAux && r == 0 && e < kNumSlabs) {
+      mbar_expect_tx(aux_bar(e), kSlabBytes);
+      tma_load_2d(x_s + buf * kSlabBytes, &tmAux, aux_bar(e), n0 + e * kSlabCols, m0);
     }
 #pragma unroll 1
-    for (int s = 0; s < kNumSlabs; ++s) {
-      const int buf = s & 1;
+    for (int s = e, it = 0; s < kNumSlabs; s += 2, ++it) {
       const int nc = n0 + s * kSlabCols;
-      if (r == 0) bulk_wait_read<1>();  // the store issued two slabs ago has drained buffer `buf`
-      named_bar_sync(1, 128);
-      if (kHasAux) {
-        if (r == 0 && s + 1 < kNumSlabs) {
-          mbar_expect_tx(aux_bar(buf ^ 1), kSlabBytes);
-          tma_load_2d(x_s + (buf ^ 1) * kSlabBytes, &tmAux, aux_bar(buf ^ 1), nc + kSlabCols, m0);
-        }
-        mbar_wait(aux_bar(buf), (s >> 1) & 1);
-      }
+      if (r == 0) bulk_wait_read<0>();  // this group's previous store has drained its slab buffers
+      named_bar_sync(1 + e, 128);
+      if (kHasAux) mbar_wait(aux_bar(e), it & 1);
       uint8_t* o0 = out0_g + buf * kSlabBytes;
       uint8_t* xb = x_g + buf * kSlabBytes;
 #pragma unroll
@@ -251,11 +247,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(2, 128);
+      named_bar_sync(3 + e, 128);
       if (r == 0) {
         if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s + buf * kSlabBytes, nc, out_row0);
         if (kHasOut1) tma_store_2d(&tmO1, x_s + buf * kSlabBytes, nc, out_row0);
         bulk_commit();
+        if (kHasAux && s + 2 < kNumSlabs) {  // the aux slab was consumed before the barrier above: refill it
+          mbar_expect_tx(aux_bar(e), kSlabBytes);
+          tma_load_2d(x_s + buf * kSlabBytes, &tmAux, aux_bar(e), nc + 2 * kSlabCols, m0);
+        }
       }
     }
     if (r == 0) bulk_wait_read<0>();
@@ -263,7 +263,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
