@@ -82,6 +82,66 @@ ln_fwd_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int64_t sc, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm forward, row-contiguous fast path (channel stride 1: token-major or channels-last input).
+// One warp per token row, the row lives in registers (each lane owns channels {2*lane + 64k, +1}): x is read
+// exactly once, two-pass mean / variance like torch's kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return make_float2(bf16_lo(w), bf16_hi(w));
+}
+
+template <typename TIn, int NCH, bool DO_LN>
+__global__ void __launch_bounds__(256)
+ln_fwd_rows_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img, int64_t T,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   __nv_bfloat16* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
+  constexpr int C = 64 * NCH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * 8 + warp; t < T; t += warps_total) {
+    const int64_t b = t / T_img;
+    const TIn* row = x + b * sb + (t - b * T_img) * st;
+    float2 v[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      v[k] = load2(row + 64 * k + 2 * lane);
+      s += v[k].x + v[k].y;
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (DO_LN) {
+      mean = warp_sum(s) * (1.0f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const float d0 = v[k].x - mean, d1 = v[k].y - mean;
+        q += d0 * d0 + d1 * d1;
+      }
+      rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+      if (lane == 0 && stats != nullptr) {
+        stats[2 * t] = mean;
+        stats[2 * t + 1] = rstd;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 64 * k + 2 * lane;
+      if (x_copy != nullptr) *reinterpret_cast<float2*>(x_copy + t * C + c) = v[k];
+      float a0 = v[k].x, a1 = v[k].y;
+      if (DO_LN) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c));
+        const float2 be = __ldg(reinterpret_cast<const float2*>(beta + c));
+        a0 = (a0 - mean) * rstd * g.x + be.x;
+        a1 = (a1 - mean) * rstd * g.y + be.y;
+      }
+      *reinterpret_cast<uint32_t*>(xn + t * C + c) = pack_bf16(a0, a1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm backward.  One warp per token row (grid-stride); each lane owns channels {2*lane + 64k, +1}.
 //   dx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat)) + dres
 //   dgamma += sum_t g * xhat,  dbeta += sum_t g
@@ -225,6 +285,33 @@ int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, i
   const double tc = static_cast<double>(B) * T_img * C;
   KernelTimer tm(st, 0.0, tc * (sizeof(TIn) + 2 + (x_copy != nullptr ? 4 : 0)), "%s_T%d_C%d",
                  gamma != nullptr ? "ln_fwd" : "convert_bf16", B * T_img, C);
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (sb % 2 == 0) && (st_ % 2 == 0);
+  if (sc == 1 && aligned) {  // rows are contiguous: warp-per-row, row held in registers, x read once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t T = static_cast<int64_t>(B) * T_img;
+    int blocks = static_cast<int>((T + 7) / 8);
+    const int cap = num_sms(dev) * 16;
+    if (blocks > cap) blocks = cap;
+    const TIn* xp = reinterpret_cast<const TIn*>(x);
+    __nv_bfloat16* xnp = reinterpret_cast<__nv_bfloat16*>(xn);
+#define CRF_LNF(NCH)                                                                                                  \
+  case NCH:                                                                                                           \
+    if (gamma != nullptr)                                                                                             \
+      ln_fwd_rows_kernel<TIn, NCH, true><<<blocks, 256, 0, st>>>(xp, sb, st_, T_img, T, gamma, beta, eps, xnp, stats, x_copy); \
+    else                                                                                                              \
+      ln_fwd_rows_kernel<TIn, NCH, false><<<blocks, 256, 0, st>>>(xp, sb, st_, T_img, T, nullptr, nullptr, eps, xnp, nullptr, x_copy); \
+    break;
+    switch (C / 64) {
+      CRF_LNF(1) CRF_LNF(2) CRF_LNF(3) CRF_LNF(4) CRF_LNF(5) CRF_LNF(6) CRF_LNF(7) CRF_LNF(8) CRF_LNF(9) CRF_LNF(10)
+      CRF_LNF(11) CRF_LNF(12) CRF_LNF(13) CRF_LNF(14) CRF_LNF(15) CRF_LNF(16)
+      default: return set_error("ln_fwd: unsupported C=%d for the row kernel", C);
+    }
+#undef CRF_LNF
+    CRF_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+  }
   if (gamma != nullptr) {
     auto k = ln_fwd_kernel<TIn, true>;
     CRF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -282,7 +369,8 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
     ln_bwd_kernel<NCH><<<blocks, 256, 0, st>>>(g, x, stats, gamma, dres, dx, dxb, dgamma, dbeta, T);         \
     break;
   switch (C / 64) {
-    CRF_LNB(1) CRF_LNB(2) CRF_LNB(4) CRF_LNB(8) CRF_LNB(16)
+    CRF_LNB(1) CRF_LNB(2) CRF_LNB(3) CRF_LNB(4) CRF_LNB(5) CRF_LNB(6) CRF_LNB(7) CRF_LNB(8) CRF_LNB(9) CRF_LNB(10)
+    CRF_LNB(11) CRF_LNB(12) CRF_LNB(13) CRF_LNB(14) CRF_LNB(15) CRF_LNB(16)
     default: return set_error("ln_bwd: unsupported C=%d", C);
   }
 #undef CRF_LNB
