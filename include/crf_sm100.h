@@ -165,6 +165,7 @@ typedef struct crf_gemm_args {
   int32_t device;
   void* workspace;         /* CRF_EPI_SPLITK_F32: fp32 partial tiles (crf_gemm_workspace_bytes) or NULL */
   size_t workspace_bytes;
+  float* colsum;           /* MN-major A only: colsum[m] += sum_k A(m,k) (bias gradient fused into wgrad), or NULL */
 } crf_gemm_args;
 int crf_gemm(const crf_gemm_args* a, void* stream);
 /* workspace a CRF_EPI_SPLITK_F32 GEMM of this shape wants (0 when it runs as a single split) */

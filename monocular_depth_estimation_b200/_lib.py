@@ -65,6 +65,7 @@ class GemmArgs(C.Structure):
         ("scale", C.c_float), ("scale_cols", C.c_int32),
         ("device", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("colsum", C.c_void_p),
     ]
 
 

@@ -108,13 +108,14 @@ int gemm_dgrad(const void* dY, const void* W, int M, int N, int K, int epi, void
   return launch_gemm(a, st);
 }
 // dW[M=Cout, N=Cin] += dY[T, Cout]^T * X[T, Cin]
-int gemm_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, void* ws, size_t ws_bytes, int device,
-               cudaStream_t st) {
+int gemm_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, float* db, void* ws, size_t ws_bytes,
+               int device, cudaStream_t st) {
   crf_gemm_args a{};
   a.A = dY; a.B = X; a.a_major = 1; a.b_major = 1;
   a.M = M; a.N = N; a.K = K; a.epilogue = CRF_EPI_SPLITK_F32; a.split_k = 0;
   a.out0 = dW; a.ld_out = N; a.scale = 1.f; a.device = device;
   a.workspace = ws; a.workspace_bytes = ws_bytes;
+  a.colsum = db;  // bias gradient = column sums of dY, computed by the same kernel
   return launch_gemm(a, st);
 }
 
@@ -232,24 +233,20 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
   // ---- MLP ----
   if (launch_cast_bf16(dy, Wk + W.dyb, static_cast<int64_t>(T) * C, st)) return 1;
   if (gemm_dgrad(Wk + W.dyb, S + L.wb_fc2, T, 4 * C, C, CRF_EPI_MUL_DGELU, Wk + W.dhpre, S + L.pre, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dyb, S + L.act, C, 4 * C, T, g->fc2_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_colsum_bf16(Wk + W.dyb, g->fc2_b, T, C, st)) return 1;
+  if (gemm_wgrad(Wk + W.dyb, S + L.act, C, 4 * C, T, g->fc2_w, g->fc2_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (gemm_dgrad(Wk + W.dhpre, S + L.wb_fc1, T, C, 4 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_colsum_bf16(Wk + W.dhpre, g->fc1_b, T, 4 * C, st)) return 1;
+  if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, g->fc1_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_ln_bwd(dxn, reinterpret_cast<const float*>(S + L.x1), reinterpret_cast<const float*>(S + L.stats2),
                     p->norm2_w, dy, dx1, Wk + W.dx1b, g->norm2_w, g->norm2_b, T, C, st))
     return 1;
   // ---- attention ----
   if (gemm_dgrad(Wk + W.dx1b, S + L.wb_proj, T, C, C, CRF_EPI_STORE_BF16, Wk + W.dob, nullptr, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_colsum_bf16(Wk + W.dx1b, g->proj_b, T, C, st)) return 1;
+  if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, g->proj_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, reinterpret_cast<const float*>(S + L.lse),
                       Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st))
     return 1;
   if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_colsum_bf16(Wk + W.dqk, g->qk_b, T, 2 * C, st)) return 1;
+  if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, g->qk_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, nullptr,
                     g->norm1_w, g->norm1_b, T, C, st))
     return 1;

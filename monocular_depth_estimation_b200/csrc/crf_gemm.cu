@@ -43,6 +43,7 @@ struct EpiParams {
   int scale_cols;
   int m_pad;       // split-K: rows per split in the partial buffer
   int store_out0;  // BIAS_GELU: 0 -> skip the pre-activation output (inference)
+  float* colsum;   // wgrad only: colsum[m] += sum_k A(m,k)  (the bias gradient), or nullptr
 };
 
 __device__ __forceinline__ void add_bias32(float (&v)[32], const float* bias, int n) {
@@ -71,7 +72,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int a_major, int b_major, EpiParams ep) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  // Bias gradient for free: one extra N=16 MMA per K step against an all-ones B tile puts sum_k A(m,k) into 16
+  // spare TMEM columns (every column holds the same sum); needs the next power of two of TMEM columns.
+  const bool do_colsum = ep.colsum != nullptr && blockIdx.y == 0;
+  const uint32_t kTmemCols = ep.colsum != nullptr ? 2u * BN : (BN < 32 ? 32u : static_cast<uint32_t>(BN));
   constexpr bool kOutF32 = (EPI == CRF_EPI_STORE_F32 || EPI == CRF_EPI_BIAS_RES_F32 || EPI == CRF_EPI_SPLITK_F32);
   constexpr bool kHasAux = (EPI == CRF_EPI_BIAS_RES_F32 || EPI == CRF_EPI_MUL_DGELU);
   constexpr bool kHasOut1 = (EPI == CRF_EPI_BIAS_GELU);
@@ -101,6 +105,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   auto aux_bar = [&](int s) { return bar_base + 8u * (2 * stages + 1 + s); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * stages + 3);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + ring_bytes + 8 * (2 * stages + 3));
+  const uint32_t ones_addr = bar_base + 8u * (2 * stages + 4);  // 1 KB of bf16 1.0 (any UMMA layout of it is all ones)
+  if (ep.colsum != nullptr && threadIdx.x < 64) {
+    *reinterpret_cast<uint4*>(smem_gen + ring_bytes + 8 * (2 * stages + 4) + 16 * threadIdx.x) =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -167,6 +177,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bd = (b_major == 0) ? make_smem_desc(b_src + ks * 32, 16, 1024, kSwizzle128)
                                              : make_smem_desc(b_src + ks * 2048, 8192, 1024, kSwizzle128);
           umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          if (do_colsum)  // K-major, no swizzle: 8x16-byte core matrices, 128 B apart along K, 256 B along N
+            umma_bf16(tmem_base + BN, ad, make_smem_desc(ones_addr, 128, 256, kSwizzleNone),
+                      make_idesc(1u, static_cast<uint32_t>(a_major), 0u, BM, 16), (i > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
       }
@@ -259,6 +272,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
     if (r == 0) bulk_wait_read<0>();
+    if (do_colsum && e == 0) {  // warp-uniform: group 0 drains the spare accumulator columns
+      uint32_t cs[32];
+      tmem_ld32(taddr + BN, cs);
+      tmem_ld_wait();
+      if (m0 + r < M) atomicAdd(ep.colsum + m0 + r, __uint_as_float(cs[0]));
+    }
   }
 
   tc_fence_before();
@@ -301,10 +320,10 @@ int launch_one(const Launch& L, const crf_gemm_args& a, cudaStream_t st) {
   if (stages > L.cps) stages = L.cps < 2 ? 2 : L.cps;
   size_t ring = static_cast<size_t>(stages) * kStageBytes;
   if (ring < 4u * kSlabBytes) ring = 4u * kSlabBytes;
-  const size_t smem = ring + 1024 + 8 * (2 * stages + 4);
+  const size_t smem = ring + 1024 + 8 * (2 * stages + 4) + 1024;  // + align slack, barriers, ones tile
   auto kern = gemm_kernel<BN, EPI>;
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  EpiParams ep{a.bias, a.scale, a.scale_cols, L.m_pad, a.out0 != nullptr ? 1 : 0};
+  EpiParams ep{a.bias, a.scale, a.scale_cols, L.m_pad, a.out0 != nullptr ? 1 : 0, a.a_major == 1 ? a.colsum : nullptr};
   dim3 grid((a.M + BM - 1) / BM, a.N / BN, L.splits);
   const double mn = static_cast<double>(a.M) * a.N;
   const double out_bytes = EPI == CRF_EPI_STORE_BF16 ? 2 * mn

@@ -49,7 +49,7 @@ def make_desc(B, H, W, Cdim, num_heads, shift, *, window=7, training=1, device=0
 
 
 def gemm(A, B, M, N, K, *, a_major=0, b_major=0, epilogue=L.EPI_STORE_F32, out0, out1=None, bias=None, aux1=None,
-         ld_out=None, scale=1.0, scale_cols=0, split_k=0):
+         ld_out=None, scale=1.0, scale_cols=0, split_k=0, colsum=None):
     a = L.GemmArgs()
     a.A, a.B = A.data_ptr(), B.data_ptr()
     a.a_major, a.b_major = a_major, b_major
@@ -62,6 +62,7 @@ def gemm(A, B, M, N, K, *, a_major=0, b_major=0, epilogue=L.EPI_STORE_F32, out0,
     a.ld_out = N if ld_out is None else ld_out
     a.scale, a.scale_cols = scale, scale_cols
     a.device = _dev(A)
+    a.colsum = colsum.data_ptr() if colsum is not None else None
     ws = None
     if epilogue == L.EPI_SPLITK_F32:
         need = L.lib().crf_gemm_workspace_bytes(M, N, K, a.device)

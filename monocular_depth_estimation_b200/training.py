@@ -57,8 +57,14 @@ def wrap_ddp(model, device, world):
     if world <= 1:
         return model
     from torch.nn.parallel import DistributedDataParallel as DDP
+    # The reference keeps torchvision's ImageNet classifier head inside the encoder module although forward() never
+    # uses it (model_mobileV3_large_newCRFs.py:176-182).  DDP requires every trainable parameter to receive a
+    # gradient, so those parameters are frozen (they never get a gradient in the reference either).
+    for name, p in model.named_parameters():
+        if ".original_model.classifier." in name:
+            p.requires_grad_(False)
     if device.type == "cuda":
-        return DDP(model, device_ids=[device.index], gradient_as_bucket_view=True, bucket_cap_mb=64)
+        return DDP(model, device_ids=[device.index], bucket_cap_mb=64)
     return DDP(model)
 
 

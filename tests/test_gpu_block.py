@@ -174,3 +174,48 @@ def test_full_model_dropin_matches_oracle_model():
     err = rel_l2(yc, yo)
     _report("full model 224x288", {"depth": err})
     assert err < TOL, err
+
+
+def test_config5_highres_inference_vs_oracle():
+    """BASELINE.json configs[4]: 960x1280 inference, batch 16 -> scale 1/4 is 240x320 (245x322 padded, 25 760
+    windows per block).  Forward only, no saved tensors; oracle evaluated with torch on the GPU (same oracle code)."""
+    pkg = _pkg()
+    torch.manual_seed(5)
+    B, H, W, C, nH = 16, 240, 320, 128, 4
+    layer = pkg.BasicCRFLayer(dim=C, depth=2, num_heads=nH, v_dim=C).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV).flatten(2).transpose(1, 2)
+    v = torch.randn(B, C, H, W, device=DEV).permute(0, 2, 3, 1)
+    with torch.no_grad():
+        y = layer(x, v, H, W)[0]
+        blocks = [{k: p.detach() for k, p in blk.named_parameters()} for blk in layer.blocks]
+        yo = torch.cat([O.basic_crf_layer(x[i:i + 4], v[i:i + 4], H, W, blocks, nH) for i in range(0, B, 4)])
+    torch.cuda.synchronize()
+    err = rel_l2(y, yo)
+    _report("config5 B16 240x320 C128 inference", {"y": err})
+    assert err < TOL, err
+
+
+def test_batch_permutation_equivariance_is_bit_exact():
+    """Size-independent property at the full config-2 shape: windows never cross images, so permuting the images of
+    the batch must permute outputs and input gradients bit-exactly (different CTAs / tiles, same arithmetic)."""
+    pkg = _pkg()
+    torch.manual_seed(6)
+    B, H, W, C, nH = 8, 120, 160, 128, 4
+    layer = pkg.BasicCRFLayer(dim=C, depth=2, num_heads=nH, v_dim=C).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV)
+    v = torch.randn(B, C, H, W, device=DEV)
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device=DEV)
+
+    def run(xi, vi):
+        xt = xi.flatten(2).transpose(1, 2).detach().requires_grad_(True)
+        vt = vi.permute(0, 2, 3, 1).detach().requires_grad_(True)
+        y = layer(xt, vt, H, W)[0]
+        y.square().sum().backward()
+        return y.detach(), xt.grad, vt.grad
+
+    y0, dx0, dv0 = run(x, v)
+    y1, dx1, dv1 = run(x[perm].contiguous(), v[perm].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(y0[perm], y1)
+    assert torch.equal(dx0[perm], dx1)
+    assert torch.equal(dv0[perm], dv1)

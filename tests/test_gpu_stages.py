@@ -81,9 +81,11 @@ def test_gemm_wgrad(M, N, K, split):
     ops, L = _ops(), _L()
     A, B = _rand_bf16(K, M, seed=5), _rand_bf16(K, N, seed=6, scale=K ** -0.5)
     out = torch.ones(M, N, device=DEV)        # accumulate semantics: starts non-zero
-    ops.gemm(A, B, M, N, K, a_major=1, b_major=1, epilogue=L.EPI_SPLITK_F32, out0=out, split_k=split)
+    db = torch.ones(M, device=DEV)            # fused bias gradient: db[m] += sum_k A[k, m]
+    ops.gemm(A, B, M, N, K, a_major=1, b_major=1, epilogue=L.EPI_SPLITK_F32, out0=out, split_k=split, colsum=db)
     torch.cuda.synchronize()
     _check(out - 1.0, A.float().t() @ B.float(), 2e-5, f"wgrad {M}x{N}x{K} split {split}")
+    _check(db - 1.0, A.float().sum(0), 2e-5, f"wgrad colsum {M}x{N}x{K} split {split}")
 
 
 def test_gemm_epilogues():
