@@ -71,7 +71,7 @@ class ClockSampler:
         try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -172,7 +172,7 @@ def run_ours(args):
     mf = torch.channels_last if args.memory_format == "channels_last" else torch.contiguous_format
     model = model.to(memory_format=mf)
     net = wrap_ddp(model, device, world)
-    opt = torch.optim.Adam(model.parameters(), 1e-4)
+    opt = torch.optim.Adam(model.parameters(), 1e-4, fused=True)  # same update as train.py:41, one fused kernel
 
     image_h = torch.rand(B, 3, H, W).contiguous(memory_format=mf).pin_memory()
     depth_h = torch.rand(B, 1, H, W).pin_memory()
@@ -300,6 +300,9 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # rank 0 must print exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference(args)
     else:

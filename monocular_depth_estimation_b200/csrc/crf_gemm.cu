@@ -24,6 +24,8 @@
 //
 // Split-K (weight gradients): each split stores its fp32 partial tile into a workspace [splits][Mpad][N] and a
 // second kernel reduces the partials into dW (+=): deterministic, and no per-element L2 atomics.
+#include <stdlib.h>
+
 #include "crf_host.h"
 #include "crf_ptx.cuh"
 
@@ -316,7 +318,11 @@ template <int BN, int EPI>
 int launch_one(const Launch& L, const crf_gemm_args& a, cudaStream_t st) {
   constexpr int kStageBytes = kATileBytes + BN * 128;
   // 2 co-resident CTAs/SM when K is short; one deep ring when K is long.
-  int stages = (L.cps >= 8) ? (BN == 256 ? 4 : 6) : (BN == 256 ? 2 : 3);
+  // wgrad: one CTA per SM streams a long token range -> deep ring.  fprop/dgrad: these are epilogue-bound (GELU,
+  // conversions, HBM stores), so favour residency: 128-wide tiles with a 2-stage ring = 3 CTAs per SM whose
+  // main loops and epilogues interleave (measured: -0.5 ms per training step vs 256-wide tiles, 2 CTAs per SM).
+  int stages = a.a_major == 1 ? ((L.cps >= 8) ? (BN == 256 ? 4 : 6) : (BN == 256 ? 2 : 3)) : 2;
+  if (const char* e = getenv("CRF_GEMM_STAGES")) stages = atoi(e);  // development knob
   if (stages > L.cps) stages = L.cps < 2 ? 2 : L.cps;
   size_t ring = static_cast<size_t>(stages) * kStageBytes;
   if (ring < 4u * kSlabBytes) ring = 4u * kSlabBytes;
@@ -384,7 +390,12 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   CRF_CHECK(a.a_major == 1 || a.K % 8 == 0, "crf_gemm: K-major A needs K %% 8 == 0 (K=%d)", a.K);
   CRF_CHECK(a.a_major == 0 || a.M % 8 == 0, "crf_gemm: MN-major A needs M %% 8 == 0 (M=%d)", a.M);
   CRF_CHECK(a.ld_out == a.N, "crf_gemm: outputs must be dense (ld_out == N)");
-  const int BN = (a.N % 256 == 0) ? 256 : (a.N % 128 == 0 ? 128 : 64);
+  int BN = (a.N % 256 == 0) ? 256 : (a.N % 128 == 0 ? 128 : 64);
+  if (a.a_major == 0 && BN > 128) BN = 128;
+  if (const char* e = getenv("CRF_GEMM_BN")) {  // development knob: cap the tile width
+    const int cap = atoi(e);
+    if (a.epilogue != CRF_EPI_SPLITK_F32 && (cap == 64 || cap == 128) && cap < BN) BN = cap;
+  }
 
   Launch L{};
   if (a.a_major == 0) {

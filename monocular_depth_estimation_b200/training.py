@@ -64,7 +64,9 @@ def wrap_ddp(model, device, world):
         if ".original_model.classifier." in name:
             p.requires_grad_(False)
     if device.type == "cuda":
-        return DDP(model, device_ids=[device.index], bucket_cap_mb=64)
+        # broadcast_buffers=False: BatchNorm running statistics stay rank-local (46 BN layers would otherwise add a
+        # broadcast of ~140 small buffers to every forward); gradients are what is averaged.
+        return DDP(model, device_ids=[device.index], bucket_cap_mb=64, broadcast_buffers=False)
     return DDP(model)
 
 
