@@ -190,13 +190,15 @@ int crf_cast_bf16(const float* src, void* dst, int64_t n, int device, void* stre
  *   o    bf16 (T, C)   attention output in token order (window_reverse + un-roll + crop applied)
  *   lse  f32 (B*nW, nH, 64) row log-sum-exp (saved for backward)
  *   qk_bias f32 (2C): q/k of zero-padded tokens are their bias (newcrf_layers.py:215,118) */
+/*   mask  optional additive mask f32 (mask_windows, 49, 49) applied to window (global index % mask_windows), as
+ *         WindowAttention.forward's `mask` argument (newcrf_layers.py:129-133); NULL / 0 for none */
 int crf_attn_fwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                 const float* rpb_table, void* o, float* lse, void* stream);
+                 const float* rpb_table, const float* mask, int mask_windows, void* o, float* lse, void* stream);
 /*   dout bf16 (T, C); dqk bf16 (T, 2C) (dq includes the scale factor); dv f32 (T, C) (= or +=);
  *   d_table f32 (169, nH) +=;  d_qk_bias f32 (2C) += (only the k half receives pad-token gradient) */
 int crf_attn_bwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                 const float* rpb_table, const float* lse, const void* dout, void* dqk, float* dv,
-                 int dv_accumulate, float* d_table, float* d_qk_bias, void* stream);
+                 const float* rpb_table, const float* mask, int mask_windows, const float* lse, const void* dout,
+                 void* dqk, float* dv, int dv_accumulate, float* d_table, float* d_qk_bias, void* stream);
 
 #ifdef __cplusplus
 }

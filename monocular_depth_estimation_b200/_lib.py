@@ -94,8 +94,8 @@ def _declare(lib):
     lib.crf_ln_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.crf_colsum_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.crf_cast_bf16.argtypes = [vp, vp, i64, i32, vp]
-    lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp]
-    lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp]
+    lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
         if name not in ("crf_last_error", "crf_kernel_launches", "crf_timing_report", "crf_gemm_workspace_bytes"):
             getattr(lib, name).restype = i32

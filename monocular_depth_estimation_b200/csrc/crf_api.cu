@@ -188,7 +188,7 @@ int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void
                  p->qk_scale, C, d->device, st))
     return 1;
   // window attention core
-  if (launch_attn_fwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, S + L.attn_o,
+  if (launch_attn_fwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, nullptr, 0, S + L.attn_o,
                       d->training ? reinterpret_cast<float*>(S + L.lse) : nullptr, st))
     return 1;
   // x1 = x + proj(attn)
@@ -242,7 +242,8 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
   // ---- attention ----
   if (gemm_dgrad(Wk + W.dx1b, S + L.wb_proj, T, C, C, CRF_EPI_STORE_BF16, Wk + W.dob, nullptr, dev, st)) return 1;
   if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, g->proj_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, reinterpret_cast<const float*>(S + L.lse),
+  if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, nullptr, 0,
+                      reinterpret_cast<const float*>(S + L.lse),
                       Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st))
     return 1;
   if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
@@ -308,20 +309,21 @@ int crf_cast_bf16(const float* src, void* dst, int64_t n, int device, void* stre
 }
 
 int crf_attn_fwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                 const float* rpb_table, void* o, float* lse, void* stream) {
+                 const float* rpb_table, const float* mask, int mask_windows, void* o, float* lse, void* stream) {
   if (check_desc(d)) return 1;
   DeviceGuard guard(d->device);
   CRF_CHECK(guard.ok, "cannot select device %d", d->device);
-  return launch_attn_fwd(*d, qk, vb, qk_bias, scale, rpb_table, o, lse, static_cast<cudaStream_t>(stream));
+  return launch_attn_fwd(*d, qk, vb, qk_bias, scale, rpb_table, mask, mask_windows, o, lse,
+                         static_cast<cudaStream_t>(stream));
 }
 int crf_attn_bwd(const crf_block_desc* d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                 const float* rpb_table, const float* lse, const void* dout, void* dqk, float* dv,
-                 int dv_accumulate, float* d_table, float* d_qk_bias, void* stream) {
+                 const float* rpb_table, const float* mask, int mask_windows, const float* lse, const void* dout,
+                 void* dqk, float* dv, int dv_accumulate, float* d_table, float* d_qk_bias, void* stream) {
   if (check_desc(d)) return 1;
   DeviceGuard guard(d->device);
   CRF_CHECK(guard.ok, "cannot select device %d", d->device);
-  return launch_attn_bwd(*d, qk, vb, qk_bias, scale, rpb_table, lse, dout, dqk, dv, dv_accumulate, d_table,
-                         d_qk_bias, static_cast<cudaStream_t>(stream));
+  return launch_attn_bwd(*d, qk, vb, qk_bias, scale, rpb_table, mask, mask_windows, lse, dout, dqk, dv,
+                         dv_accumulate, d_table, d_qk_bias, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -130,6 +130,8 @@ attn_fwd_kernel(const AttnParams P) {
         for (int j = 0; j < kNTok; ++j) {
           float s = __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]) + tbl[bi - rpb_col(j)];
           if (masked && rrow[j] != my_region) s += -100.0f;
+          if (P.ext_mask != nullptr)
+            s += __ldg(P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok + j);
           p[j] = s;
           mx = fmaxf(mx, s);
         }
@@ -316,6 +318,8 @@ attn_bwd_kernel(const AttnParams P) {
           for (int j = 0; j < kNTok; ++j) {
             float s = __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]) + tbl[bi - rpb_col(j)];
             if (masked && rrow[j] != my_region) s += -100.0f;
+            if (P.ext_mask != nullptr)
+              s += __ldg(P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok + j);
             p[j] = __expf(s - lse);
           }
         } else {
@@ -465,7 +469,7 @@ static bool use_legacy_attn() {
 }
 
 int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                    const float* table, void* o, float* lse, cudaStream_t st) {
+                    const float* table, const float* ext_mask, int ext_mask_nw, void* o, float* lse, cudaStream_t st) {
   AttnParams P{};
   if (fill_attn_params(P, d)) return 1;
   P.qk = reinterpret_cast<const __nv_bfloat16*>(qk);
@@ -473,6 +477,8 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.qk_bias = qk_bias;
   P.table = table;
   P.scale = scale;
+  P.ext_mask = ext_mask_nw > 0 ? ext_mask : nullptr;
+  P.ext_mask_nw = ext_mask_nw > 0 ? ext_mask_nw : 1;
   P.o = reinterpret_cast<__nv_bfloat16*>(o);
   P.lse = lse;
   if (!use_legacy_attn()) return launch_attn_fwd_pipe(P, d, st);
@@ -491,8 +497,8 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
 }
 
 int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                    const float* table, const float* lse, const void* dout, void* dqk, float* dv, int dv_acc,
-                    float* d_table, float* d_qk_bias, cudaStream_t st) {
+                    const float* table, const float* ext_mask, int ext_mask_nw, const float* lse, const void* dout,
+                    void* dqk, float* dv, int dv_acc, float* d_table, float* d_qk_bias, cudaStream_t st) {
   AttnParams P{};
   if (fill_attn_params(P, d)) return 1;
   P.qk = reinterpret_cast<const __nv_bfloat16*>(qk);
@@ -500,6 +506,8 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.qk_bias = qk_bias;
   P.table = table;
   P.scale = scale;
+  P.ext_mask = ext_mask_nw > 0 ? ext_mask : nullptr;
+  P.ext_mask_nw = ext_mask_nw > 0 ? ext_mask_nw : 1;
   P.lse = const_cast<float*>(lse);
   P.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   P.dqk = reinterpret_cast<__nv_bfloat16*>(dqk);

@@ -19,6 +19,8 @@ struct AttnParams {
   const float* qk_bias;      // (2C)
   const float* table;        // (169, nH)
   float scale;
+  const float* ext_mask;     // optional additive mask (nwm, 49, 49) f32, window index = global window % nwm; or nullptr
+  int ext_mask_nw;
   // forward
   __nv_bfloat16* o;          // (T, C)
   float* lse;                // (B*nW, nH, 64)

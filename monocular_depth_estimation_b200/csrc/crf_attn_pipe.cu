@@ -238,6 +238,9 @@ attn_bwd_pipe_kernel(const AttnParams P) {
       const int wg = wg_s[g * 128 + r];
       const uint8_t* rrow = rid_s + g * 128 + half * 64;
       const int my_region = rrow[pos];
+      const float* xmask = (P.ext_mask != nullptr && tok != -2)
+                               ? P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok
+                               : nullptr;
       mbar_wait(bars.s_done(g), n & 1);
       tc_fence_after();
       float p[64], ds[64];
@@ -252,6 +255,7 @@ attn_bwd_pipe_kernel(const AttnParams P) {
           for (int j = 0; j < kNTok; ++j) {
             float s = __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]) + tbl[bi - rpb_col(j)];
             if (masked && rrow[j] != my_region) s += -100.0f;
+            if (xmask != nullptr) s += __ldg(xmask + j);
             p[j] = __expf(s - lse);
           }
         } else {
@@ -464,6 +468,9 @@ attn_fwd_pipe_kernel(const AttnParams P) {
       const int wg = wg_s[g * 128 + r];
       const uint8_t* rrow = rid_s + g * 128 + half * 64;
       const int my_region = rrow[pos];
+      const float* xmask = (P.ext_mask != nullptr && tok != -2)
+                               ? P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok
+                               : nullptr;
       mbar_wait(bars.s_done(g), n & 1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
@@ -477,6 +484,7 @@ attn_fwd_pipe_kernel(const AttnParams P) {
         for (int j = 0; j < kNTok; ++j) {
           float s = __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]) + tbl[bi - rpb_col(j)];
           if (masked && rrow[j] != my_region) s += -100.0f;
+          if (xmask != nullptr) s += __ldg(xmask + j);
           p[j] = s;
           mx = fmaxf(mx, s);
         }

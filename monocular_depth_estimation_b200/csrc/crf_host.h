@@ -85,9 +85,9 @@ int launch_window_scatter(const float* windows, float* x, int B, int H, int W, i
                           cudaStream_t st);
 int launch_shift_mask(float* mask, int H, int W, int window, int shift, cudaStream_t st);
 int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                    const float* table, void* o, float* lse, cudaStream_t st);
+                    const float* table, const float* ext_mask, int ext_mask_nw, void* o, float* lse, cudaStream_t st);
 int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                    const float* table, const float* lse, const void* dout, void* dqk, float* dv, int dv_acc,
-                    float* d_table, float* d_qk_bias, cudaStream_t st);
+                    const float* table, const float* ext_mask, int ext_mask_nw, const float* lse, const void* dout,
+                    void* dqk, float* dv, int dv_acc, float* d_table, float* d_qk_bias, cudaStream_t st);
 
 }  // namespace crf

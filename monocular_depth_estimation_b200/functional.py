@@ -116,3 +116,58 @@ def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None
     if qk_scale is None:
         qk_scale = (Cd // num_heads) ** -0.5
     return _CRFBlockFn.apply(x, v, v_bf16, H, W, num_heads, window, shift, float(qk_scale), float(eps), *params)
+
+
+class _WindowAttentionFn(torch.autograd.Function):
+    """Stand-alone WindowAttention.forward (newcrf_layers.py:110-149) on already-partitioned windows, built from the
+    stage-level entry points: qk GEMM -> attention core (each window = a 7x7 image, no pad, no shift) -> proj GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, v, mask, num_heads, scale, qk_w, qk_b, table, proj_w, proj_b):
+        from . import ops
+        B_, N, Cd = x.shape
+        T = B_ * N
+        dev = x.device
+        xb = x.detach().reshape(T, Cd).to(torch.bfloat16).contiguous()
+        vb = v.detach().reshape(T, Cd).to(torch.bfloat16).contiguous()
+        wqk, wp = ops.cast_bf16(qk_w.detach().contiguous()), ops.cast_bf16(proj_w.detach().contiguous())
+        qkb, pb = qk_b.detach().contiguous(), proj_b.detach().contiguous()
+        tab = table.detach().contiguous()
+        m = None if mask is None else mask.detach().float().contiguous()
+        desc = make_desc(B_, 7, 7, Cd, num_heads, 0, device=dev.index)
+        qk = torch.empty(T, 2 * Cd, dtype=torch.bfloat16, device=dev)
+        ops.gemm(xb, wqk, T, 2 * Cd, Cd, epilogue=L.EPI_STORE_BF16, out0=qk, bias=qkb, scale=scale, scale_cols=Cd)
+        o, lse = ops.attn_fwd(desc, qk, vb, qkb, scale, tab, want_lse=True, mask=m)
+        out = torch.empty(T, Cd, dtype=torch.float32, device=dev)
+        ops.gemm(o, wp, T, Cd, Cd, epilogue=L.EPI_STORE_F32, out0=out, bias=pb)
+        ctx.save_for_backward(xb, vb, wqk, wp, qkb, tab, qk, o, lse, m if m is not None else torch.empty(0, device=dev))
+        ctx.meta = (B_, N, Cd, num_heads, scale, m is not None)
+        return out.view(B_, N, Cd)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        xb, vb, wqk, wp, qkb, tab, qk, o, lse, m = ctx.saved_tensors
+        B_, N, Cd, num_heads, scale, has_mask = ctx.meta
+        T, dev = B_ * N, xb.device
+        desc = make_desc(B_, 7, 7, Cd, num_heads, 0, device=dev.index)
+        dob = ops.cast_bf16(dout.contiguous().float().reshape(T, Cd))
+        d_o = torch.empty(T, Cd, dtype=torch.bfloat16, device=dev)
+        ops.gemm(dob, wp, T, Cd, Cd, b_major=1, epilogue=L.EPI_STORE_BF16, out0=d_o)
+        d_wp, d_pb = torch.zeros(Cd, Cd, device=dev), torch.zeros(Cd, device=dev)
+        ops.gemm(dob, o, Cd, Cd, T, a_major=1, b_major=1, epilogue=L.EPI_SPLITK_F32, out0=d_wp, colsum=d_pb)
+        dqk, dv, d_tab, d_qkb = ops.attn_bwd(desc, qk, vb, qkb, scale, tab, lse, d_o, mask=m if has_mask else None)
+        dx = torch.empty(T, Cd, dtype=torch.float32, device=dev)
+        ops.gemm(dqk, wqk, T, Cd, 2 * Cd, b_major=1, epilogue=L.EPI_STORE_F32, out0=dx)
+        d_wqk = torch.zeros(2 * Cd, Cd, device=dev)
+        ops.gemm(dqk, xb, 2 * Cd, Cd, T, a_major=1, b_major=1, epilogue=L.EPI_SPLITK_F32, out0=d_wqk, colsum=d_qkb)
+        return (dx.view(B_, N, Cd), dv.view(B_, N, Cd), None, None, None, d_wqk, d_qkb, d_tab, d_wp, d_pb)
+
+
+def window_attention(x, v, qk_w, qk_b, table, proj_w, proj_b, num_heads, scale, mask=None):
+    """WindowAttention.forward(x, v, mask): x, v (num_windows*B, 49, C); mask (nW, 49, 49) or None -> (B_, 49, C) fp32."""
+    assert x.dim() == 3 and x.shape[1] == 49, "window attention expects (num_windows*B, 49, C) windows of 7x7 tokens"
+    assert x.shape[-1] == v.shape[-1], "self.dim != v.shape[-1]"
+    if not x.is_cuda:
+        raise RuntimeError("monocular_depth_estimation_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    return _WindowAttentionFn.apply(x, v, mask, num_heads, float(scale), qk_w, qk_b, table, proj_w, proj_b)

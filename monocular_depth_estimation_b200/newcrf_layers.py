@@ -6,7 +6,7 @@ reference keep working:
 
     reference class (file:line)                 here
     Mlp                  newcrf_layers.py:9      Mlp              (parameter holder; math runs inside the fused block)
-    WindowAttention      newcrf_layers.py:62     WindowAttention  (parameter holder + stand-alone forward)
+    WindowAttention      newcrf_layers.py:62     WindowAttention.forward(x, v, mask) on pre-partitioned windows (stage-level kernels)
     CRFBlock             newcrf_layers.py:152    CRFBlock.forward(x, v, mask_matrix) with .H/.W set by the caller
     BasicCRFLayer        newcrf_layers.py:260    BasicCRFLayer.forward(x, v, H, W) -> (x, H, W, x, H, W)
     NewCRF               newcrf_layers.py:367    NewCRF.forward(x_nchw, v_nchw) -> nchw
@@ -79,6 +79,13 @@ class WindowAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
         self.softmax = nn.Softmax(dim=-1)
+
+    def forward(self, x, v, mask=None):
+        """x, v: (num_windows*B, 49, C) pre-partitioned windows; mask: (nW, 49, 49) additive or None.
+        The fused CRFBlock never materialises windows and does not call this; it exists for drop-in use of the class
+        on its own (qk GEMM -> attention core -> proj GEMM through the stage-level entry points)."""
+        return CF.window_attention(x, v, self.qk.weight, self.qk.bias, self.relative_position_bias_table,
+                                   self.proj.weight, self.proj.bias, self.num_heads, self.scale, mask)
 
 
 class CRFBlock(nn.Module):

@@ -146,24 +146,25 @@ def shift_mask(H, W, window, shift, device):
     return out
 
 
-def attn_fwd(desc, qk, vb, qk_bias, scale, table, want_lse=True):
+def attn_fwd(desc, qk, vb, qk_bias, scale, table, want_lse=True, mask=None):
     T, Cd = vb.shape
     Hp, Wp = -(-desc.H // 7) * 7, -(-desc.W // 7) * 7
     nW = (Hp // 7) * (Wp // 7)
     o = torch.zeros(T, Cd, dtype=torch.bfloat16, device=vb.device)
     lse = torch.zeros(desc.B * nW, desc.num_heads, 64, dtype=torch.float32, device=vb.device) if want_lse else None
-    L.check(L.lib().crf_attn_fwd(C.byref(desc), _ptr(qk), _ptr(vb), _ptr(qk_bias), scale, _ptr(table), _ptr(o),
-                                 _ptr(lse), _stream(vb)), "crf_attn_fwd")
+    L.check(L.lib().crf_attn_fwd(C.byref(desc), _ptr(qk), _ptr(vb), _ptr(qk_bias), scale, _ptr(table), _ptr(mask),
+                                 0 if mask is None else mask.shape[0], _ptr(o), _ptr(lse), _stream(vb)),
+            "crf_attn_fwd")
     return o, lse
 
 
-def attn_bwd(desc, qk, vb, qk_bias, scale, table, lse, dout):
+def attn_bwd(desc, qk, vb, qk_bias, scale, table, lse, dout, mask=None):
     T, Cd = vb.shape
     dqk = torch.zeros(T, 2 * Cd, dtype=torch.bfloat16, device=vb.device)
     dv = torch.zeros(T, Cd, dtype=torch.float32, device=vb.device)
     d_table = torch.zeros_like(table)
     d_bias = torch.zeros_like(qk_bias)
-    L.check(L.lib().crf_attn_bwd(C.byref(desc), _ptr(qk), _ptr(vb), _ptr(qk_bias), scale, _ptr(table), _ptr(lse),
-                                 _ptr(dout), _ptr(dqk), _ptr(dv), 0, _ptr(d_table), _ptr(d_bias), _stream(vb)),
-            "crf_attn_bwd")
+    L.check(L.lib().crf_attn_bwd(C.byref(desc), _ptr(qk), _ptr(vb), _ptr(qk_bias), scale, _ptr(table), _ptr(mask),
+                                 0 if mask is None else mask.shape[0], _ptr(lse), _ptr(dout), _ptr(dqk), _ptr(dv), 0,
+                                 _ptr(d_table), _ptr(d_bias), _stream(vb)), "crf_attn_bwd")
     return dqk, dv, d_table, d_bias

@@ -219,3 +219,36 @@ def test_batch_permutation_equivariance_is_bit_exact():
     assert torch.equal(y0[perm], y1)
     assert torch.equal(dx0[perm], dx1)
     assert torch.equal(dv0[perm], dv1)
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_window_attention_standalone_matches_oracle(with_mask):
+    """WindowAttention.forward(x, v, mask) on pre-partitioned windows (newcrf_layers.py:110-149), incl. an arbitrary
+    additive mask indexed by window-within-image."""
+    pkg = _pkg()
+    torch.manual_seed(11)
+    C, nH, nW, B = 128, 4, 6, 3
+    wa = pkg.WindowAttention(C, (7, 7), nH, C).to(DEV)
+    with torch.no_grad():
+        wa.relative_position_bias_table.normal_(0, 0.3)
+        wa.qk.bias.normal_(0, 0.2)
+    x = torch.randn(B * nW, 49, C, device=DEV, requires_grad=True)
+    v = torch.randn(B * nW, 49, C, device=DEV, requires_grad=True)
+    mask = None
+    if with_mask:
+        mask = torch.where(torch.rand(nW, 49, 49, device=DEV) < 0.3, -100.0, 0.0)
+        mask[:, torch.arange(49), torch.arange(49)] = 0.0
+    dy = torch.randn(B * nW, 49, C, device=DEV)
+    y = wa(x, v, mask)
+    y.backward(dy)
+    p = {"attn." + k: t.detach().clone().requires_grad_(True) for k, t in wa.named_parameters()}
+    xo, vo = x.detach().clone().requires_grad_(True), v.detach().clone().requires_grad_(True)
+    yo = O.window_attention(xo, vo, p, nH, mask)
+    yo.backward(dy)
+    torch.cuda.synchronize()
+    errs = {"y": rel_l2(y.detach(), yo.detach()), "dx": rel_l2(x.grad, xo.grad), "dv": rel_l2(v.grad, vo.grad)}
+    for k, t in wa.named_parameters():
+        errs[k] = rel_l2(t.grad, p["attn." + k].grad)
+    _report(f"window_attention standalone mask={with_mask}", errs)
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, f"{bad}\nall: {errs}"
