@@ -26,8 +26,7 @@
 // second kernel reduces the partials into dW (+=): deterministic, and no per-element L2 atomics.
 #include <stdlib.h>
 
-#include "crf_host.h"
-#include "crf_ptx.cuh"
+#include "crf_gemm_epi.cuh"
 
 namespace crf {
 
@@ -38,33 +37,6 @@ constexpr int BK = 64;
 constexpr int kThreads = 320;  // 8 epilogue warps (two groups of 4), 1 TMA warp, 1 MMA warp
 constexpr int kATileBytes = BM * 128;  // 16 KB
 constexpr int kSlabBytes = BM * 128;   // 16 KB: 128 rows x 128 B
-
-struct EpiParams {
-  const float* bias;
-  float scale;
-  int scale_cols;
-  int m_pad;       // split-K: rows per split in the partial buffer
-  int store_out0;  // BIAS_GELU: 0 -> skip the pre-activation output (inference)
-  float* colsum;   // wgrad only: colsum[m] += sum_k A(m,k)  (the bias gradient), or nullptr
-};
-
-__device__ __forceinline__ void add_bias32(float (&v)[32], const float* bias, int n) {
-  if (bias == nullptr) return;
-  const float4* b4 = reinterpret_cast<const float4*>(bias + n);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(b4 + j);
-    v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-  }
-}
-// 32 fp32 values -> 4 x 16-byte chunks of bf16 at chunk index c0.. of row r of a swizzled slab
-__device__ __forceinline__ void store_bf16_32(uint8_t* slab, int r, int c0, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<uint4*>(slab + sw128_offset(r, c0 + j)) =
-        make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads)
@@ -218,48 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t acc[32];
         tmem_ld32(taddr + s * kSlabCols + half * 32, acc);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        const int n = nc + half * 32;
-        if constexpr (EPI == CRF_EPI_STORE_F32 || EPI == CRF_EPI_SPLITK_F32) {
-          add_bias32(v, ep.bias, n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(o0 + sw128_offset(r, j)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if constexpr (EPI == CRF_EPI_BIAS_RES_F32) {
-          add_bias32(v, ep.bias, n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 q = *reinterpret_cast<const float4*>(xb + sw128_offset(r, j));
-            *reinterpret_cast<float4*>(o0 + sw128_offset(r, j)) =
-                make_float4(v[4 * j] + q.x, v[4 * j + 1] + q.y, v[4 * j + 2] + q.z, v[4 * j + 3] + q.w);
-          }
-        } else if constexpr (EPI == CRF_EPI_STORE_BF16) {
-          add_bias32(v, ep.bias, n);
-          if (n < ep.scale_cols) {  // scale_cols is a multiple of 32: a 32-column group is on one side
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.scale;
-          }
-          store_bf16_32(o0, r, half * 4, v);
-        } else if constexpr (EPI == CRF_EPI_BIAS_GELU) {
-          add_bias32(v, ep.bias, n);
-          if (ep.store_out0) store_bf16_32(o0, r, half * 4, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          store_bf16_32(xb, r, half * 4, v);
-        } else if constexpr (EPI == CRF_EPI_MUL_DGELU) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 p = *reinterpret_cast<const uint4*>(xb + sw128_offset(r, half * 4 + j));
-            v[8 * j + 0] *= dgelu_erf(bf16_lo(p.x)); v[8 * j + 1] *= dgelu_erf(bf16_hi(p.x));
-            v[8 * j + 2] *= dgelu_erf(bf16_lo(p.y)); v[8 * j + 3] *= dgelu_erf(bf16_hi(p.y));
-            v[8 * j + 4] *= dgelu_erf(bf16_lo(p.z)); v[8 * j + 5] *= dgelu_erf(bf16_hi(p.z));
-            v[8 * j + 6] *= dgelu_erf(bf16_lo(p.w)); v[8 * j + 7] *= dgelu_erf(bf16_hi(p.w));
-          }
-          store_bf16_32(o0, r, half * 4, v);
-        }
+        epi_group32<EPI>(acc, ep, nc + half * 32, r, half, o0, xb);
       }
       fence_proxy_async_smem();
       named_bar_sync(3 + e, 128);
@@ -390,6 +321,13 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   CRF_CHECK(a.a_major == 1 || a.K % 8 == 0, "crf_gemm: K-major A needs K %% 8 == 0 (K=%d)", a.K);
   CRF_CHECK(a.a_major == 0 || a.M % 8 == 0, "crf_gemm: MN-major A needs M %% 8 == 0 (M=%d)", a.M);
   CRF_CHECK(a.ld_out == a.N, "crf_gemm: outputs must be dense (ld_out == N)");
+  {  // token-major projections with N % 128 == 0 run on the persistent kernel (crf_gemm_persist.cu)
+    static const bool persist = !(getenv("CRF_GEMM_PERSIST") && atoi(getenv("CRF_GEMM_PERSIST")) == 0);
+    if (persist) {
+      const int rc = launch_gemm_persistent(a, st);
+      if (rc >= 0) return rc;
+    }
+  }
   int BN = (a.N % 256 == 0) ? 256 : (a.N % 128 == 0 ? 128 : 64);
   if (a.a_major == 0 && BN > 128) BN = 128;
   if (const char* e = getenv("CRF_GEMM_BN")) {  // development knob: cap the tile width
