@@ -166,10 +166,12 @@ int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void
   const bool plain = x_is_plain(*d);
 
   // bf16 operand copies of the four weight matrices (kept in `saved`: backward reuses them)
-  if (launch_cast_bf16(p->qk_w, S + L.wb_qk, 2LL * C * C, st)) return 1;
-  if (launch_cast_bf16(p->proj_w, S + L.wb_proj, 1LL * C * C, st)) return 1;
-  if (launch_cast_bf16(p->fc1_w, S + L.wb_fc1, 4LL * C * C, st)) return 1;
-  if (launch_cast_bf16(p->fc2_w, S + L.wb_fc2, 4LL * C * C, st)) return 1;
+  {
+    const float* const src[4] = {p->qk_w, p->proj_w, p->fc1_w, p->fc2_w};
+    void* const dst[4] = {S + L.wb_qk, S + L.wb_proj, S + L.wb_fc1, S + L.wb_fc2};
+    const long long n[4] = {2LL * C * C, 1LL * C * C, 4LL * C * C, 4LL * C * C};
+    if (launch_cast4_bf16(src, dst, n, st)) return 1;
+  }
 
   // LN1 (+ layout change of the NCHW view into token-major rows)
   float* xc = plain ? nullptr : reinterpret_cast<float*>(S + L.xc);

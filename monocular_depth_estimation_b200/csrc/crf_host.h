@@ -78,6 +78,7 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
                   float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
 int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st);
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
+int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long long n[4], cudaStream_t st);
 int launch_convert_tokens(const void* src, int dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
                           void* dst_bf16, cudaStream_t st);
 int launch_window_gather(const float* x, float* windows, int B, int H, int W, int C, int window, int shift,

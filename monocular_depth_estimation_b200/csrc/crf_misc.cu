@@ -244,6 +244,27 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 
+// four fp32 -> bf16 casts in one launch (the weight matrices of a block); blockIdx.y selects the tensor
+struct Cast4 {
+  const float* src[4];
+  __nv_bfloat16* dst[4];
+  long long n[4];
+};
+__global__ void __launch_bounds__(256) cast4_bf16_kernel(const Cast4 c) {
+  const float* __restrict__ src = c.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ dst = c.dst[blockIdx.y];
+  const long long n = c.n[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * 256 * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+      *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // stand-alone window gather / scatter / mask (bit-exact index tests)
 // ------------------------------------------------------------------------------------------------
@@ -401,6 +422,29 @@ int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
   KernelTimer tm(st, 0.0, 6.0 * n, "cast_bf16_n%lld", static_cast<long long>(n));
   cast_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  CRF_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long long n[4], cudaStream_t st) {
+  Cast4 c;
+  long long nmax = 0, total = 0;
+  for (int i = 0; i < 4; ++i) {
+    c.src[i] = src[i];
+    c.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst[i]);
+    c.n[i] = n[i];
+    if (n[i] > nmax) nmax = n[i];
+    total += n[i];
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  long long gx = (nmax / 4 + 255) / 256;
+  const long long cap = num_sms(dev) * 4;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  KernelTimer tm(st, 0.0, 6.0 * total, "cast4_bf16_n%lld", total);
+  cast4_bf16_kernel<<<dim3(static_cast<unsigned>(gx), 4), 256, 0, st>>>(c);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

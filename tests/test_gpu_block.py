@@ -252,3 +252,55 @@ def test_window_attention_standalone_matches_oracle(with_mask):
     _report(f"window_attention standalone mask={with_mask}", errs)
     bad = {k: e for k, e in errs.items() if not e < TOL}
     assert not bad, f"{bad}\nall: {errs}"
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 1, 1), (1, 3, 5), (1, 7, 7), (3, 8, 13), (2, 6, 50), (5, 14, 7), (1, 20, 29)])
+def test_ragged_geometries_vs_oracle(B, H, W):
+    """Edge geometries: maps smaller than one window (all-pad windows but one), exact multiples of 7 (no padding),
+    odd numbers of windows (the last window pair is half empty), token counts that are not multiples of the 128-row
+    GEMM tile.  Two blocks (shift 0 and 3), fwd + bwd, vs the fp32 oracle."""
+    pkg = _pkg()
+    torch.manual_seed(B * 1000 + H * 31 + W)
+    C, nH = 64, 2
+    layer = pkg.BasicCRFLayer(dim=C, depth=2, num_heads=nH, v_dim=C).to(DEV)
+    with torch.no_grad():
+        for p in layer.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, C, H, W, device=DEV).flatten(2).transpose(1, 2).requires_grad_(True)
+    v = torch.randn(B, C, H, W, device=DEV).permute(0, 2, 3, 1).requires_grad_(True)
+    dy = torch.randn(B, H * W, C, device=DEV)
+    y = layer(x, v, H, W)[0]
+    y.backward(dy)
+    blocks = [{k: p.detach().clone().requires_grad_(True) for k, p in blk.named_parameters()} for blk in layer.blocks]
+    xo, vo = x.detach().clone().requires_grad_(True), v.detach().clone().requires_grad_(True)
+    yo = O.basic_crf_layer(xo, vo, H, W, blocks, nH)
+    yo.backward(dy)
+    torch.cuda.synchronize()
+    errs = {"y": rel_l2(y.detach(), yo.detach()), "dx": rel_l2(x.grad, xo.grad), "dv": rel_l2(v.grad, vo.grad)}
+    for i, blk in enumerate(layer.blocks):
+        for k, p in blk.named_parameters():
+            errs[f"{i}.{k}"] = rel_l2(p.grad, blocks[i][k].grad)
+    _report(f"ragged B{B} {H}x{W}", errs)
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, f"{bad}\nall: {errs}"
+
+
+def test_c_api_rejects_bad_arguments():
+    """Error behaviour of the C ABI itself: non-zero return + message, no crash, no kernel launch."""
+    import ctypes as C
+    from monocular_depth_estimation_b200 import _lib, ops
+    lib = _lib.lib()
+    d = ops.make_desc(1, 7, 7, 64, 2, 0, device=0)
+    assert lib.crf_block_fwd(C.byref(d), None, None, None, None, None, None, 0, None) != 0
+    assert b"null pointer" in lib.crf_last_error()
+    d.num_heads = 4  # head_dim 16: not implemented
+    s = C.c_size_t()
+    assert lib.crf_block_sizes(C.byref(d), C.byref(s), None, None) != 0
+    assert b"head_dim must be 32" in lib.crf_last_error()
+    a = _lib.GemmArgs()
+    x = torch.zeros(128, 64, dtype=torch.bfloat16, device=DEV)
+    a.A, a.B, a.out0 = x.data_ptr(), x.data_ptr(), x.data_ptr()
+    a.M, a.N, a.K, a.ld_out = 128, 96, 64, 96   # N not a multiple of 64
+    assert lib.crf_gemm(C.byref(a), None) != 0
+    assert b"multiple of 64" in lib.crf_last_error()
