@@ -10,11 +10,14 @@
 //   warp   12    MMA issuer        one thread issues every tcgen05.mma; owns the TMEM allocation
 //   (warps 13-15 only fill the fourth warpgroup so setmaxnreg can re-balance registers)
 //
-// Hand-offs are mbarriers (counts in parentheses): full[g] (128 loader arrivals) -> s_done[g] (tcgen05.commit) ->
-// p_ready[g] (128 compute arrivals) -> o_done[g] (tcgen05.commit; also frees the input tiles for the loaders) ->
-// t_free[g] (128 compute arrivals: TMEM columns drained).  The MMA thread issues  S(i), then the second-stage MMAs
-// of pair i-1, so one lane's tensor work and the other lane's softmax math overlap, and the gathers of pair i+2
-// overlap both.
+// Hand-offs are mbarriers (counts in parentheses): full[g][slot] (128 loader arrivals) -> s_done[g]
+// (tcgen05.commit) -> p_ready[g] (128 compute arrivals) -> o_done[g] (tcgen05.commit) -> t_free[g] (128 compute
+// arrivals: TMEM columns drained).  Each lane has TWO input slots, so the gathers of a lane's next pair run while
+// its current pair is still in the tensor / softmax stages; a slot is handed back to the loaders by in_free[g][slot]
+// (a second tcgen05.commit after the pair's last MMA).  The MMA thread issues S(i), then the second-stage MMAs of
+// pair i-1, so one lane's tensor work overlaps the other lane's softmax math.  The backward needs 64 KB of
+// block-diagonal P / dS tiles per lane, so it runs with ONE input slot per lane (sharing one tile set between the
+// lanes was measured slower: it chains every pair's tile write behind the previous pair's MMAs).
 #include "crf_attn_common.cuh"
 
 namespace crf {
@@ -39,40 +42,51 @@ constexpr int kPipeThreads = 512;
 constexpr int HD = 32;
 
 // ---- shared-memory plan (offsets from the 1024-aligned base) ----
-// backward: in[g] = Q,K,V,dO (4 x 8 KB); tiles[g] = Pbd (32 KB) + dSbd (32 KB)
-constexpr uint32_t kBwdIn = 0;                         // 2 x 32 KB
-constexpr uint32_t kBwdTiles = 65536;                  // 2 x 64 KB
-constexpr uint32_t kBwdMisc = 65536 + 131072;          // 196608
-// forward: in[g] = Q,K,V (3 x 8 KB, padded to 32 KB); tiles[g] = P (16 KB)
-constexpr uint32_t kFwdIn = 0;                         // 2 x 32 KB
-constexpr uint32_t kFwdTiles = 65536;                  // 2 x 16 KB
-constexpr uint32_t kFwdMisc = 65536 + 32768;           // 98304
-// misc block: tbl[176] f32 | tok[2][128] i32 | wgl[2][128] i32 | rid[2][128] u8 | barriers[10] | tmem ptr
+// backward: in[g][0] = Q,K,V,dO (4 x 8 KB); P/dS tiles (2 x 32 KB) per lane: lane 0 in the tile area, lane 1 in the
+// input slots [0][1] and [1][1], which the backward leaves unused
+constexpr uint32_t kBwdIn = 0;                         // 4 x 32 KB
+constexpr uint32_t kBwdTiles = 131072;                 // 64 KB
+constexpr uint32_t kBwdMisc = 131072 + 65536;          // 196608
+// forward: in[g][slot] = Q,K,V (3 x 8 KB, padded to 32 KB) x 4; tiles[g] = P (16 KB)
+constexpr uint32_t kFwdIn = 0;                         // 4 x 32 KB
+constexpr uint32_t kFwdTiles = 131072;                 // 2 x 16 KB
+constexpr uint32_t kFwdMisc = 131072 + 32768;          // 163840
+// misc block: tbl[176] f32 | tok[4][128] i32 | wgl[4][128] i32 | rid[4][128] u8 | barriers[17] | tmem ptr
 constexpr uint32_t kMiscTbl = 0;
 constexpr uint32_t kMiscTok = 704;
-constexpr uint32_t kMiscWg = 704 + 1024;
-constexpr uint32_t kMiscRid = 704 + 2048;
-constexpr uint32_t kMiscBar = 704 + 2048 + 256;        // 3008, 8-byte aligned
-constexpr uint32_t kMiscTmem = kMiscBar + 10 * 8;
+constexpr uint32_t kMiscWg = 704 + 2048;
+constexpr uint32_t kMiscRid = 704 + 4096;
+constexpr uint32_t kMiscBar = 704 + 4096 + 512;        // 5312, 8-byte aligned
+constexpr uint32_t kMiscTmem = kMiscBar + 17 * 8;
 constexpr uint32_t kMiscBytes = kMiscTmem + 16;
+
+// backward tile placement: lane 0 uses the dedicated tile area, lane 1 the two input slots the backward does not use
+__host__ __device__ constexpr uint32_t bwd_p_tile(int g) { return g == 0 ? kBwdTiles : kBwdIn + 1 * 32768; }
+__host__ __device__ constexpr uint32_t bwd_ds_tile(int g) { return g == 0 ? kBwdTiles + 32768 : kBwdIn + 3 * 32768; }
 
 struct Bars {
   uint32_t base;
-  __device__ uint32_t full(int g) const { return base + 8u * g; }
-  __device__ uint32_t s_done(int g) const { return base + 8u * (2 + g); }
-  __device__ uint32_t p_ready(int g) const { return base + 8u * (4 + g); }
-  __device__ uint32_t o_done(int g) const { return base + 8u * (6 + g); }
-  __device__ uint32_t t_free(int g) const { return base + 8u * (8 + g); }
+  __device__ uint32_t full(int g, int slot) const { return base + 8u * (2 * g + slot); }
+  __device__ uint32_t s_done(int g) const { return base + 8u * (4 + g); }
+  __device__ uint32_t p_ready(int g) const { return base + 8u * (6 + g); }
+  __device__ uint32_t o_done(int g) const { return base + 8u * (8 + g); }
+  __device__ uint32_t t_free(int g) const { return base + 8u * (10 + g); }
+  __device__ uint32_t in_free(int g, int slot) const { return base + 8u * (12 + 2 * g + slot); }
+  __device__ uint32_t tiles_free() const { return base + 8u * 16; }
 };
 
 __device__ __forceinline__ void init_bars(const Bars& b) {
   for (int g = 0; g < 2; ++g) {
-    mbar_init(b.full(g), 128);
+    for (int slot = 0; slot < 2; ++slot) {
+      mbar_init(b.full(g, slot), 128);
+      mbar_init(b.in_free(g, slot), 1);
+    }
     mbar_init(b.s_done(g), 1);
     mbar_init(b.p_ready(g), 128);
     mbar_init(b.o_done(g), 1);
     mbar_init(b.t_free(g), 128);
   }
+  mbar_init(b.tiles_free(), 1);
   fence_mbar_init();
 }
 
@@ -160,9 +174,9 @@ attn_bwd_pipe_kernel(const AttnParams P) {
       const uint32_t idesc_t = make_idesc(1u, 1u, 1u, 128, HD);   // dV, dK: MN-major x MN-major
       const uint32_t idesc_q = make_idesc(1u, 0u, 1u, 128, HD);   // dQ    : K-major x MN-major
       auto second_stage = [&](int g2, int n2) {
-        const uint32_t in = base + kBwdIn + g2 * 32768;
+        const uint32_t in = base + kBwdIn + (2 * g2) * 32768;
         const uint32_t Qs = in, Ks = in + 8192, Gs = in + 24576;
-        const uint32_t Pb = base + kBwdTiles + g2 * 65536, Db = Pb + 32768;
+        const uint32_t Pb = base + bwd_p_tile(g2), Db = base + bwd_ds_tile(g2);
         const uint32_t t0 = tmem + g2 * 256;
         mbar_wait(bars.p_ready(g2), n2 & 1);
         tc_fence_after();
@@ -178,14 +192,15 @@ attn_bwd_pipe_kernel(const AttnParams P) {
         for (int ks = 0; ks < 8; ++ks)  // dQ = dSbd [K_A;K_B] : K = 128 stacked keys
           umma_bf16(t0 + 64, make_smem_desc(Db + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kSwizzle128),
                     make_smem_desc(Ks + ks * 1024, 512, 512, kSwizzle64), idesc_q, ks > 0 ? 1u : 0u);
-        umma_commit(bars.o_done(g2));
+        umma_commit(bars.o_done(g2));        // results ready for the compute group
+        umma_commit(bars.in_free(g2, 0));    // the lane's input tiles may be refilled
       };
       for (int i = 0; i < niter; ++i) {
         const int g = i & 1, n = i >> 1;
-        const uint32_t in = base + kBwdIn + g * 32768;
+        const uint32_t in = base + kBwdIn + (2 * g) * 32768;
         const uint32_t Qs = in, Ks = in + 8192, Vs = in + 16384, Gs = in + 24576;
         const uint32_t t0 = tmem + g * 256;
-        mbar_wait(bars.full(g), n & 1);
+        mbar_wait(bars.full(g, 0), n & 1);
         if (n > 0) mbar_wait(bars.t_free(g), (n - 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -209,13 +224,14 @@ attn_bwd_pipe_kernel(const AttnParams P) {
     int pair = blockIdx.x;
     for (int i = 0; i < niter; ++i, pair += gridDim.x) {
       const int g = i & 1, n = i >> 1;
-      if (n > 0) mbar_wait(bars.o_done(g), (n - 1) & 1);  // previous pair of this lane has finished reading in[g]
-      load_pair<true>(P, pair, r, pi, pj, h, base + kBwdIn + g * 32768, gen + kBwdIn + g * 32768, tok_s + g * 128,
-                      wg_s + g * 128, rid_s + g * 128);
+      const int b4 = 2 * g;  // backward: one input slot per lane (the other two slots hold lane 1's P / dS tiles)
+      if (n >= 1) mbar_wait(bars.in_free(g, 0), (n - 1) & 1);  // the lane's previous pair is done with the tiles
+      load_pair<true>(P, pair, r, pi, pj, h, base + kBwdIn + b4 * 32768, gen + kBwdIn + b4 * 32768, tok_s + b4 * 128,
+                      wg_s + b4 * 128, rid_s + b4 * 128);
       cp_async_commit();
       cp_async_wait_all();
       fence_proxy_async_smem();
-      mbar_arrive(bars.full(g));
+      mbar_arrive(bars.full(g, 0));
     }
   } else {
     // ================= compute groups =================
@@ -224,8 +240,8 @@ attn_bwd_pipe_kernel(const AttnParams P) {
     const int r = threadIdx.x & 127;
     const int half = r >> 6, pos = r & 63;
     const uint32_t t0 = tmem + g * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    uint8_t* Pb_g = gen + kBwdTiles + g * 65536;
-    uint8_t* Db_g = Pb_g + 32768;
+    uint8_t* Pb_g = gen + bwd_p_tile(g);
+    uint8_t* Db_g = gen + bwd_ds_tile(g);
     const int bi = rpb_base(pos < kNTok ? pos : 0);
     const bool masked = P.gm.shift > 0;
     float dtab[kNTok];
@@ -233,10 +249,11 @@ attn_bwd_pipe_kernel(const AttnParams P) {
     for (int j = 0; j < kNTok; ++j) dtab[j] = 0.f;
 
     for (int i = g, n = 0; i < niter; i += 2, ++n) {
-      mbar_wait(bars.full(g), n & 1);
-      const int tok = tok_s[g * 128 + r];
-      const int wg = wg_s[g * 128 + r];
-      const uint8_t* rrow = rid_s + g * 128 + half * 64;
+      const int b4 = 2 * g;
+      mbar_wait(bars.full(g, 0), n & 1);
+      const int tok = tok_s[b4 * 128 + r];
+      const int wg = wg_s[b4 * 128 + r];
+      const uint8_t* rrow = rid_s + b4 * 128 + half * 64;
       const int my_region = rrow[pos];
       const float* xmask = (P.ext_mask != nullptr && tok != -2)
                                ? P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok
@@ -409,7 +426,7 @@ attn_fwd_pipe_kernel(const AttnParams P) {
       const uint32_t idesc_s = make_idesc(1u, 0u, 0u, 128, 128);
       const uint32_t idesc_o = make_idesc(1u, 0u, 1u, 128, HD);
       auto second_stage = [&](int g2, int n2) {  // O = P V: window A -> cols [0,hd), window B -> [hd,2hd)
-        const uint32_t Vs = base + kFwdIn + g2 * 32768 + 16384;
+        const uint32_t Vs = base + kFwdIn + (2 * g2 + (n2 & 1)) * 32768 + 16384;
         const uint32_t Ps = base + kFwdTiles + g2 * 16384;
         const uint32_t t0 = tmem + g2 * 128;
         mbar_wait(bars.p_ready(g2), n2 & 1);
@@ -421,11 +438,12 @@ attn_fwd_pipe_kernel(const AttnParams P) {
             umma_bf16(t0 + half * HD, make_smem_desc(Ps + ks * 32, 16, 1024, kSwizzle128),
                       make_smem_desc(Vs + half * 4096 + ks * 1024, 512, 512, kSwizzle64), idesc_o, ks > 0 ? 1u : 0u);
         umma_commit(bars.o_done(g2));
+        umma_commit(bars.in_free(g2, n2 & 1));
       };
       for (int i = 0; i < niter; ++i) {
         const int g = i & 1, n = i >> 1;
-        const uint32_t Qs = base + kFwdIn + g * 32768, Ks = Qs + 8192;
-        mbar_wait(bars.full(g), n & 1);
+        const uint32_t Qs = base + kFwdIn + (2 * g + (n & 1)) * 32768, Ks = Qs + 8192;
+        mbar_wait(bars.full(g, n & 1), (n >> 1) & 1);
         if (n > 0) mbar_wait(bars.t_free(g), (n - 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -444,13 +462,14 @@ attn_fwd_pipe_kernel(const AttnParams P) {
     int pair = blockIdx.x;
     for (int i = 0; i < niter; ++i, pair += gridDim.x) {
       const int g = i & 1, n = i >> 1;
-      if (n > 0) mbar_wait(bars.o_done(g), (n - 1) & 1);
-      load_pair<false>(P, pair, r, pi, pj, h, base + kFwdIn + g * 32768, gen + kFwdIn + g * 32768, tok_s + g * 128,
-                       wg_s + g * 128, rid_s + g * 128);
+      const int slot = n & 1, b4 = 2 * g + slot;
+      if (n >= 2) mbar_wait(bars.in_free(g, slot), ((n >> 1) - 1) & 1);
+      load_pair<false>(P, pair, r, pi, pj, h, base + kFwdIn + b4 * 32768, gen + kFwdIn + b4 * 32768, tok_s + b4 * 128,
+                       wg_s + b4 * 128, rid_s + b4 * 128);
       cp_async_commit();
       cp_async_wait_all();
       fence_proxy_async_smem();
-      mbar_arrive(bars.full(g));
+      mbar_arrive(bars.full(g, slot));
     }
   } else {
     reg_alloc<200>();
@@ -463,10 +482,11 @@ attn_fwd_pipe_kernel(const AttnParams P) {
     const bool masked = P.gm.shift > 0;
 
     for (int i = g, n = 0; i < niter; i += 2, ++n) {
-      mbar_wait(bars.full(g), n & 1);
-      const int tok = tok_s[g * 128 + r];
-      const int wg = wg_s[g * 128 + r];
-      const uint8_t* rrow = rid_s + g * 128 + half * 64;
+      const int b4 = 2 * g + (n & 1);
+      mbar_wait(bars.full(g, n & 1), (n >> 1) & 1);
+      const int tok = tok_s[b4 * 128 + r];
+      const int wg = wg_s[b4 * 128 + r];
+      const uint8_t* rrow = rid_s + b4 * 128 + half * 64;
       const int my_region = rrow[pos];
       const float* xmask = (P.ext_mask != nullptr && tok != -2)
                                ? P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok

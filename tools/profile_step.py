@@ -16,12 +16,15 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default="gpurun_out/step_profile.txt")
+    ap.add_argument("--cudnn-benchmark", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    model = PTModel().to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), 1e-4)
-    img, dep = torch.rand(a.batch, 3, 480, 640, device=dev), torch.rand(a.batch, 1, 480, 640, device=dev)
+    torch.backends.cudnn.benchmark = a.cudnn_benchmark
+    model = PTModel().to(dev).train().to(memory_format=torch.channels_last)
+    opt = torch.optim.Adam(model.parameters(), 1e-4, fused=True)
+    img = torch.rand(a.batch, 3, 480, 640, device=dev).contiguous(memory_format=torch.channels_last)
+    dep = torch.rand(a.batch, 1, 480, 640, device=dev)
     for _ in range(3):
         train_step(model, opt, img, dep)
     torch.cuda.synchronize()
