@@ -31,6 +31,16 @@ METRIC = "train_images_per_sec_480x640"
 UNIT = "img/s"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Write the ONE JSON line to the process's real stdout (see main(): fd 1 is pointed at stderr while working so
+    that banners printed by native libraries, e.g. 'NCCL version ...', cannot end up in front of it)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -43,8 +53,9 @@ def parse_args():
     ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel timing table (JSON) to this file")
-    ap.add_argument("--cuda-graph", type=int, default=1,
-                    help="1: capture the whole training step (fwd+loss+bwd+Adam) in a CUDA graph at N=1 and replay it")
+    ap.add_argument("--cuda-graph", type=int, default=2,
+                    help="1: capture the whole training step (fwd+loss+bwd+Adam) in a CUDA graph at N=1 and replay it; "
+                         "2: also at N>1 (DDP all-reduce captured in the graph); 0: eager")
     ap.add_argument("--memory-format", default="channels_last", choices=["contiguous", "channels_last"],
                     help="memory format of the model and the images (host-side choice; math is identical)")
     return ap.parse_args()
@@ -147,7 +158,7 @@ def run_reference(args):
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -165,6 +176,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback "
                          "(use --impl reference for the CPU reference arm)")
     lib = _lib.lib()  # fail loudly if the extension is missing
+    graph_multi = bool(args.cuda_graph >= 2 and int(os.environ.get("WORLD_SIZE", "1")) > 1)
+    if graph_multi:  # whole-step capture with DDP (PyTorch CUDA-graph notes): no async NCCL error handling
+        os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
     rank, local_rank, world, device = init_distributed()
     torch.cuda.set_device(device)
     torch.manual_seed(1234 + rank)
@@ -173,9 +187,17 @@ def run_ours(args):
     model = PTModel().to(device).train()
     mf = torch.channels_last if args.memory_format == "channels_last" else torch.contiguous_format
     model = model.to(memory_format=mf)
-    net = wrap_ddp(model, device, world)
+    use_graph = bool(args.cuda_graph and (world == 1 or graph_multi))
+    if graph_multi:  # DDP must be constructed on the side stream the warm-up and capture will use
+        side0 = torch.cuda.Stream()
+        side0.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side0):
+            net = wrap_ddp(model, device, world)
+        torch.cuda.current_stream().wait_stream(side0)
+    else:
+        net = wrap_ddp(model, device, world)
     # same update as train.py:41 in one fused kernel; capturable so the step can live in a CUDA graph
-    opt = torch.optim.Adam(model.parameters(), 1e-4, fused=True, capturable=bool(args.cuda_graph and world == 1))
+    opt = torch.optim.Adam(model.parameters(), 1e-4, fused=True, capturable=use_graph)
 
     image_h = torch.rand(B, 3, H, W).contiguous(memory_format=mf).pin_memory()
     depth_h = torch.rand(B, 1, H, W).pin_memory()
@@ -211,12 +233,12 @@ def run_ours(args):
     # Whole-step CUDA graph (single GPU): ~1600 launches per step are replayed from one graph, which removes the
     # CPU launch gaps (the GPU is otherwise idle ~10 % of the step).  The captured work is the same eager step.
     graph, static_loss, launches_per_replay = None, None, 0
-    if args.cuda_graph and world == 1:
+    if use_graph:
         try:
-            side = torch.cuda.Stream()
+            side = side0 if graph_multi else torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):
+                for _ in range(11 if graph_multi else 2):  # DDP needs >= 11 eager iterations before capture
                     step_eager()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
@@ -279,9 +301,18 @@ def run_ours(args):
     lib.crf_timing_report(buf, need + 16)
     kernels = json.loads(buf.value.decode())
 
-    if rank != 0:
+    def finish():
+        # With a captured DDP step the NCCL communicator is referenced by the CUDA graph and an orderly
+        # destroy_process_group() was observed to hang at exit (after the result had been produced): leave hard.
+        torch.cuda.synchronize()
+        if graph is not None and world > 1:
+            sys.stderr.flush()
+            os._exit(0)
         if world > 1:
             dist.destroy_process_group()
+
+    if rank != 0:
+        finish()
         return
 
     peaks = load_peaks()
@@ -370,16 +401,20 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
+    finish()
 
 
 def main():
     args = parse_args()
     # rank 0 must print exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (NCCL's levels nest: WARN would still print the banner, so the variable is removed unless INFO/TRACE was asked for)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
