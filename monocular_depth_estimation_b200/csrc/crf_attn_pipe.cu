@@ -229,9 +229,16 @@ attn_bwd_pipe_kernel(const AttnParams P) {
       load_pair<true>(P, pair, r, pi, pj, h, base + kBwdIn + b4 * 32768, gen + kBwdIn + b4 * 32768, tok_s + b4 * 128,
                       wg_s + b4 * 128, rid_s + b4 * 128);
       cp_async_commit();
-      cp_async_wait_all();
+      if (i >= 1) {  // publish pair i-1 once its gathers have landed; pair i's stay in flight behind it
+        cp_async_wait_group<1>();
+        fence_proxy_async_smem();
+        mbar_arrive(bars.full((i - 1) & 1, 0));
+      }
+    }
+    if (niter >= 1) {
+      cp_async_wait_group<0>();
       fence_proxy_async_smem();
-      mbar_arrive(bars.full(g, 0));
+      mbar_arrive(bars.full((niter - 1) & 1, 0));
     }
   } else {
     // ================= compute groups =================
@@ -467,9 +474,16 @@ attn_fwd_pipe_kernel(const AttnParams P) {
       load_pair<false>(P, pair, r, pi, pj, h, base + kFwdIn + b4 * 32768, gen + kFwdIn + b4 * 32768, tok_s + b4 * 128,
                        wg_s + b4 * 128, rid_s + b4 * 128);
       cp_async_commit();
-      cp_async_wait_all();
+      if (i >= 2) {  // three pairs of gathers in flight: publish pair i-2 once it has landed
+        cp_async_wait_group<2>();
+        fence_proxy_async_smem();
+        mbar_arrive(bars.full(i & 1, ((i - 2) >> 1) & 1));
+      }
+    }
+    for (int j = niter >= 2 ? niter - 2 : 0; j < niter; ++j) {  // drain
+      if (j == niter - 1) cp_async_wait_group<0>(); else cp_async_wait_group<1>();
       fence_proxy_async_smem();
-      mbar_arrive(bars.full(g, slot));
+      mbar_arrive(bars.full(j & 1, (j >> 1) & 1));
     }
   } else {
     reg_alloc<200>();

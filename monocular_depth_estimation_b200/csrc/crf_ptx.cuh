@@ -112,6 +112,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
@@ -224,27 +226,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7; measured < 5e-7 on gelu / gelu' in fp32, three orders of
-// magnitude below the bf16 rounding of the stored result).  erff() costs ~2.5x the instructions, and the GELU
-// epilogues are issue-bound: 4C evaluations per token per block.  Also returns e = exp(-z*z) for the derivative.
-__device__ __forceinline__ float erf_as(float z, float& e) {
-  const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  e = __expf(-az * az);
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  return copysignf(fmaf(-p * t, e, 1.0f), z);
+// Exact-erf GELU (nn.GELU default, newcrf_layers.py:171) evaluated in sigmoid form:
+//   Phi(x) = (1 + erf(x / sqrt2)) / 2 = 1 / (1 + 2^(-w(x))),   w(x) = log2((1 + erf(x/sqrt2)) / erfc(x/sqrt2)),
+// w is odd and w(x) / x is fitted by a quadratic in t = min(x^2, 25) (minimax over |x| <= 9, tools/fit_gelu.py):
+// |gelu err| < 2.6e-5, |gelu' err| < 5.1e-5 absolute -- 40x below the bf16 rounding of the stored values -- for
+// 9 instructions (2 MUFU) instead of the 17 of an A&S 7.1.26 erf.  The GELU epilogues are issue-bound (4C
+// evaluations per token per block: ncu shows 66 % issue-slot utilisation on fc1 with the erf form), so this is
+// what decides whether fc1 / dgrad-fc2 run at the HBM roofline.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float gelu_erf(float x) {
-  float e;
-  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f, e));
+__device__ __forceinline__ float gelu_cdf(float x) {
+  const float t = fminf(x * x, 25.0f);
+  const float r = fmaf(fmaf(0.0010142630f, t, -0.10677572f), t, -2.3011212f);  // -w(x)/x
+  return __fdividef(1.0f, 1.0f + ex2_approx(x * r));
 }
-__device__ __forceinline__ float dgelu_erf(float x) {  // 0.5 (1 + erf(x/sqrt2)) + x exp(-x^2/2) / sqrt(2 pi)
-  float e;
-  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
-  return fmaf(x * 0.39894228040143268f, e, cdf);
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_cdf(x); }
+__device__ __forceinline__ float dgelu_erf(float x) {  // Phi(x) + x exp(-x^2/2) / sqrt(2 pi)
+  return fmaf(x * 0.3989422804f, ex2_approx(-0.72134752f * x * x), gelu_cdf(x));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
