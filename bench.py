@@ -332,7 +332,7 @@ def run_ours(args):
         for prefix, fam in (("gemm_fprop", "gemm_persistent_kernel (fprop+dgrad projections)"),
                             ("gemm_dgrad", "gemm_persistent_kernel (fprop+dgrad projections)"),
                             ("gemm_wgrad", "gemm_kernel (split-K weight gradients)"),
-                            ("attn_bwd", "attn_bwd_pipe_kernel"), ("attn_fwd", "attn_fwd_pipe_kernel"),
+                            ("attn_bwd", "attn_bwd_async_kernel"), ("attn_fwd", "attn_fwd_async_kernel"),
                             ("ln_bwd", "ln_bwd_kernel"), ("ln_fwd", "ln_fwd_rows_kernel"),
                             ("convert_bf16", "ln_fwd_rows_kernel"), ("splitk_reduce", "splitk_reduce_kernel"),
                             ("cast", "cast_bf16_kernel")):

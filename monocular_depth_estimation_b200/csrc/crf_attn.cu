@@ -463,8 +463,15 @@ attn_bwd_kernel(const AttnParams P) {
 
 int launch_attn_fwd_pipe(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
 int launch_attn_bwd_pipe(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
+int launch_attn_fwd_async(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
+int launch_attn_bwd_async(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
 static bool use_legacy_attn() {
   static const bool v = getenv("CRF_ATTN_LEGACY") != nullptr;  // development switch: single-buffer kernels
+  return v;
+}
+// development switch for A/B measurements: CRF_ATTN_IMPL=pipe selects the second-generation kernels (crf_attn_pipe.cu)
+static bool use_pipe_attn() {
+  static const bool v = getenv("CRF_ATTN_IMPL") != nullptr && getenv("CRF_ATTN_IMPL")[0] == 'p';
   return v;
 }
 
@@ -481,7 +488,8 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.ext_mask_nw = ext_mask_nw > 0 ? ext_mask_nw : 1;
   P.o = reinterpret_cast<__nv_bfloat16*>(o);
   P.lse = lse;
-  if (!use_legacy_attn()) return launch_attn_fwd_pipe(P, d, st);
+  P.prof = getenv("CRF_ATTN_PROF") != nullptr;
+  if (!use_legacy_attn()) return use_pipe_attn() ? launch_attn_fwd_pipe(P, d, st) : launch_attn_fwd_async(P, d, st);
   const size_t smem = 40960 + 176 * 4 + 128 + 32 + 1024;
   CRF_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int gx = (num_sms(d.device) * 4 + P.nH - 1) / P.nH;
@@ -515,7 +523,8 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.dv_acc = dv_acc;
   P.d_table = d_table;
   P.d_qk_bias = d_qk_bias;
-  if (!use_legacy_attn()) return launch_attn_bwd_pipe(P, d, st);
+  P.prof = getenv("CRF_ATTN_PROF") != nullptr;
+  if (!use_legacy_attn()) return use_pipe_attn() ? launch_attn_bwd_pipe(P, d, st) : launch_attn_bwd_async(P, d, st);
   const size_t smem = 98304 + 176 * 4 + 128 + 32 + 1024;
   CRF_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int gx = (num_sms(d.device) * 2 + P.nH - 1) / P.nH;

@@ -31,6 +31,8 @@ struct AttnParams {
   int dv_acc;
   float* d_table;            // (169, nH)
   float* d_qk_bias;          // (2C)
+  float rcp_nW, rcp_nWw;     // 1 / windows per image, 1 / windows per row (fast exact division in the kernels)
+  int prof;                  // development: block (0,0) prints per-phase cycle counts (CRF_ATTN_PROF=1)
 };
 
 // Token index of tile row r of a window pair: >= 0 real token, -1 zero-pad token, -2 dead row.

@@ -33,6 +33,9 @@ int fill_attn_params(AttnParams& P, const crf_block_desc& d) {
   P.nH = d.num_heads;
   P.total_windows = d.B * P.gm.nW;
   P.npairs = (P.total_windows + 1) / 2;
+  P.rcp_nW = 1.0f / static_cast<float>(P.gm.nW);
+  P.rcp_nWw = 1.0f / static_cast<float>(P.gm.nWw);
+  CRF_CHECK(P.total_windows < (1 << 22), "attention core: too many windows (%d)", P.total_windows);
   return 0;
 }
 

@@ -3,14 +3,14 @@
 // Same tiles, descriptors and epilogue math as gemm_kernel (crf_gemm.cu), but one CTA per SM loops over output
 // tiles and the three stages of a tile run CONCURRENTLY on different tiles:
 //
-//   warp 16        TMA producer : keeps the 3-stage A/B ring full across tile boundaries
+//   warp 16        TMA producer : keeps the 3- or 5-stage A/B ring (see Plan) full across tile boundaries
 //   warp 17        MMA issuer   : accumulates tile i into TMEM buffer i % 4 (4 x 128 columns = all 512 columns)
 //   warps 0-15     epilogue     : four groups of four warps; group g drains the tiles with i % 4 == g
 //                                 (thread = accumulator row), each group with its own output / aux slab buffers
 //
 // so the epilogue warps -- which bound these GEMMs (GELU, conversions, HBM stores) -- never wait for a main loop,
 // and barrier init / TMEM allocation / descriptor prefetch are paid once per SM instead of once per tile.
-// Barriers: full/empty[3] (TMA <-> MMA), tmem_full[4] (MMA -> epilogue, tcgen05.commit), tmem_empty[4]
+// Barriers: full/empty[stages] (TMA <-> MMA), tmem_full[4] (MMA -> epilogue, tcgen05.commit), tmem_empty[4]
 // (epilogue -> MMA, 128 arrivals), aux[4] (TMA aux-slab loads of each group).
 #include "crf_gemm_epi.cuh"
 
@@ -19,16 +19,24 @@ namespace crf {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 3;
 constexpr int kAcc = 4;
 constexpr int kThreads = 576;  // 16 epilogue warps + TMA warp + MMA warp
 constexpr int kATile = BM * 128, kBTile = BN * 128, kStage = kATile + kBTile;  // 16 KB + 16 KB
 constexpr int kSlab = BM * 128;                                                // 16 KB
-constexpr int kRing = kStages * kStage;                                        // 96 KB
-constexpr int kSlabs = kAcc * 2 * kSlab;                                       // 128 KB: per group out0 | x
-constexpr int kBarOff = kRing + kSlabs;
-constexpr int kNumBars = 2 * kStages + 3 * kAcc;
-constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024;
+// Shared-memory plan per epilogue: each of the four epilogue groups owns an output slab and, if the epilogue reads an
+// aux tile or writes a second output, a second slab; whatever is left of the 227 KB goes to the A/B ring:
+// 3 stages (96 KB) with two slabs per group, 5 stages (160 KB) with one (plain stores: qk, the dX GEMMs).
+template <int EPI>
+struct Plan {
+  static constexpr int kSlabsPerGroup = (EpiTraits<EPI>::kHasAux || EpiTraits<EPI>::kHasOut1) ? 2 : 1;
+  static constexpr int kSlabBytes = kAcc * kSlabsPerGroup * kSlab;
+  static constexpr int kStages = kSlabsPerGroup == 2 ? 3 : 5;
+  static constexpr int kRing = kStages * kStage;
+  static constexpr int kBarOff = kRing + kSlabBytes;
+  static constexpr int kNumBars = 2 * kStages + 3 * kAcc;
+  static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024;
+  static_assert(kSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
+};
 
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -36,6 +44,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep) {
   using TR = EpiTraits<EPI>;
+  using PL = Plan<EPI>;
+  constexpr int kStages = PL::kStages, kRing = PL::kRing, kBarOff = PL::kBarOff, kNumBars = PL::kNumBars;
+  constexpr int kGroupSlabs = PL::kSlabsPerGroup * kSlab;
   constexpr int kSlabCols = TR::kSlabCols;
   constexpr int kNumSlabs = BN / kSlabCols;
 
@@ -138,8 +149,8 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===== epilogue groups =====
     const int g = warp >> 2;
     const int r = threadIdx.x & 127;
-    const uint32_t out0_s = base + kRing + g * 2 * kSlab, x_s = out0_s + kSlab;
-    uint8_t* o0 = gen + kRing + g * 2 * kSlab;
+    const uint32_t out0_s = base + kRing + g * kGroupSlabs, x_s = out0_s + kSlab;  // x_s only with two slabs / group
+    uint8_t* o0 = gen + kRing + g * kGroupSlabs;
     uint8_t* xb = o0 + kSlab;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int aux_cnt = 0;
@@ -201,6 +212,7 @@ template <int EPI>
 int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO0, const CUtensorMap& tmO1,
              const CUtensorMap& tmAux, const crf_gemm_args& a, cudaStream_t st) {
   auto kern = gemm_persistent_kernel<EPI>;
+  constexpr int kSmemBytes = Plan<EPI>::kSmemBytes;
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
   int grid = num_sms(a.device);

@@ -57,6 +57,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// Non-blocking completion test (try_wait may suspend the thread for a system-dependent time: wrong for a thread that
+// polls several barriers).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // Bounded wait: a barrier that never completes is a programming error; trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -114,6 +129,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// The hardware performs one arrive on `bar` (counted against its expected arrivals: .noinc) once every cp.async this
+// thread has issued so far has completed; the thread itself does not wait.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// fire-and-forget 16-byte fp32 vector reduction into global memory (no return value, no read latency on the issuer)
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
@@ -180,6 +205,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM, same shape: thread i writes 32 consecutive fp32 columns of lane 32*(w%4)+i
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp, restated)
@@ -196,6 +234,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(swizzle & 7) << 61;
   return d;
+}
+
+// The same descriptor split into a loop-invariant part and a byte offset: the address field is (saddr >> 4) in the low
+// 14 bits, so a tile-relative offset is ONE 32-bit add on the low word (valid while base + offset stays inside shared
+// memory, i.e. below 2^18).  A single thread that issues dozens of small MMAs per tile is bound by the ~15 uniform-
+// datapath instructions the generic form costs per descriptor pair.
+struct SmemDescBase {
+  uint32_t lo, hi;
+};
+__device__ __forceinline__ SmemDescBase make_smem_desc_base(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                            uint32_t swizzle) {
+  SmemDescBase d;
+  d.lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((swizzle & 7u) << 29);
+  return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_at(const SmemDescBase& d, uint32_t byte_off) {
+  return (static_cast<uint64_t>(d.hi) << 32) | static_cast<uint64_t>(d.lo + (byte_off >> 4));
 }
 
 // kind::f16 / kind::tf32 instruction descriptor: fp32 accumulate, A/B format (1 = bf16, 2 = tf32),

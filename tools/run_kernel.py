@@ -30,7 +30,7 @@ def timed(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "block", "gemm"])
+    ap.add_argument("what", choices=["attn", "block", "gemm", "gemms"])
     ap.add_argument("--stage", type=int, default=0)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shift", type=int, default=3)
@@ -61,6 +61,24 @@ def main():
             y = blk(x, v, None)
             y.backward(torch.ones_like(y))
         print("block fwd+bwd ms", timed(step, a.iters))
+    elif a.what == "gemms":
+        # every fprop / dgrad projection shape of this stage: (label, M, N, K, b_major, epilogue)
+        shapes = [("qk", T, 2 * C, C, 0, L.EPI_STORE_BF16), ("proj+res", T, C, C, 0, L.EPI_BIAS_RES_F32),
+                  ("fc1+gelu", T, 4 * C, C, 0, L.EPI_BIAS_GELU), ("fc2+res", T, C, 4 * C, 0, L.EPI_BIAS_RES_F32),
+                  ("d_fc2*gelu'", T, 4 * C, C, 1, L.EPI_MUL_DGELU), ("d_fc1", T, C, 4 * C, 1, L.EPI_STORE_F32),
+                  ("d_proj", T, C, C, 1, L.EPI_STORE_BF16), ("d_qk", T, C, 2 * C, 1, L.EPI_STORE_F32)]
+        for name, M, N, K, bmaj, epi in shapes:
+            A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+            Wt = (torch.randn(K, N, device=dev) if bmaj else torch.randn(N, K, device=dev)).to(torch.bfloat16)
+            f32 = epi in (L.EPI_STORE_F32, L.EPI_BIAS_RES_F32)
+            out0 = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+            out1 = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if epi == L.EPI_BIAS_GELU else None
+            aux = (torch.randn(M, N, device=dev) if epi == L.EPI_BIAS_RES_F32 else
+                   torch.randn(M, N, device=dev).to(torch.bfloat16) if epi == L.EPI_MUL_DGELU else None)
+            bias = torch.randn(N, device=dev) if not bmaj else None
+            ms = timed(lambda: ops.gemm(A, Wt, M, N, K, b_major=bmaj, epilogue=epi, out0=out0, out1=out1, bias=bias,
+                                        aux1=aux), a.iters)
+            print(f"{name:12s} M{M} N{N} K{K}: {ms*1e3:8.1f} us  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s")
     else:
         M, N, K = T, 4 * C, C
         A = torch.randn(M, K, device=dev).to(torch.bfloat16)
