@@ -179,6 +179,15 @@ int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, i
 /* LayerNorm backward: dx = LN'(g) + dres; accumulates dgamma/dbeta (+=). g f32 (T,C), x f32 (T,C). */
 int crf_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres, float* dx,
                void* dx_bf16, float* dgamma, float* dbeta, int T, int C, int device, void* stream);
+/* Stand-alone LayerNorm over the channels of contiguous token rows: the `norm_crf` that closes a decoder stage
+ * (replaces nn.LayerNorm in NewCRF.forward, /root/reference/src/newcrf_layers.py:430-431).
+ *   x f32 (T, C) contiguous; y f32 or bf16 (T, C) (y_dtype = CRF_DT_F32 / CRF_DT_BF16: under bf16 autocast the next
+ *   consumer is a convolution that would cast anyway); stats f32 (T, 2) = (mean, rstd) for the backward.
+ * Backward: g = dL/dy in f32 or bf16; dx f32 (T, C); dgamma / dbeta are ACCUMULATED (+=). */
+int crf_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                      float* stats, int T, int C, int device, void* stream);
+int crf_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                      float* dgamma, float* dbeta, int T, int C, int device, void* stream);
 /* out[n] += sum_t g[t, n], g bf16 (T, N) */
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
 /* f32 -> bf16 contiguous */

@@ -299,6 +299,20 @@ int crf_ln_bwd(const float* g, const float* x, const float* stats, const float* 
   CRF_CHECK(guard.ok, "cannot select device %d", device);
   return launch_ln_bwd(g, x, stats, gamma, dres, dx, dx_bf16, dgamma, dbeta, T, C, static_cast<cudaStream_t>(stream));
 }
+int crf_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                      float* stats, int T, int C, int device, void* stream) {
+  CRF_CHECK(x && gamma && beta && y && stats && T > 0, "crf_layernorm_fwd: bad arguments");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_layernorm_fwd(x, gamma, beta, eps, y, y_dtype, stats, T, C, static_cast<cudaStream_t>(stream));
+}
+int crf_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                      float* dgamma, float* dbeta, int T, int C, int device, void* stream) {
+  CRF_CHECK(g && x && stats && gamma && dx && dgamma && dbeta && T > 0, "crf_layernorm_bwd: bad arguments");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_layernorm_bwd(g, g_dtype, x, stats, gamma, dx, dgamma, dbeta, T, C, static_cast<cudaStream_t>(stream));
+}
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream) {
   DeviceGuard guard(device);
   CRF_CHECK(guard.ok, "cannot select device %d", device);

@@ -76,6 +76,10 @@ int launch_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st_, int64_t s
                   cudaStream_t st);
 int launch_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres,
                   float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
+int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                         float* stats, int T, int C, cudaStream_t st);
+int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                         float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
 int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st);
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
 int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long long n[4], cudaStream_t st);

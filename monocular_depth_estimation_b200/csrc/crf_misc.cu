@@ -92,11 +92,16 @@ __device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
   return make_float2(bf16_lo(w), bf16_hi(w));
 }
 
-template <typename TIn, int NCH, bool DO_LN>
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<uint32_t*>(p) = pack_bf16(a, b);
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+template <typename TIn, int NCH, bool DO_LN, typename TOut = __nv_bfloat16>
 __global__ void __launch_bounds__(256)
 ln_fwd_rows_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img, int64_t T,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   __nv_bfloat16* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
+                   TOut* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
   constexpr int C = 64 * NCH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
@@ -136,7 +141,7 @@ ln_fwd_rows_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img,
         a0 = (a0 - mean) * rstd * g.x + be.x;
         a1 = (a1 - mean) * rstd * g.y + be.y;
       }
-      *reinterpret_cast<uint32_t*>(xn + t * C + c) = pack_bf16(a0, a1);
+      store2(xn + t * C + c, a0, a1);
     }
   }
 }
@@ -146,9 +151,9 @@ ln_fwd_rows_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img,
 //   dx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat)) + dres
 //   dgamma += sum_t g * xhat,  dbeta += sum_t g
 // ------------------------------------------------------------------------------------------------
-template <int NCH>  // C = 64 * NCH
+template <int NCH, typename TG = float>  // C = 64 * NCH
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
+ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, int T) {
   constexpr int C = 64 * NCH;
@@ -164,13 +169,13 @@ ln_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const fl
   const int warps_total = gridDim.x * 8;
   for (int t = blockIdx.x * 8 + warp; t < T; t += warps_total) {
     const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
-    const float* gr = g + static_cast<int64_t>(t) * C;
+    const TG* gr = g + static_cast<int64_t>(t) * C;
     const float* xr = x + static_cast<int64_t>(t) * C;
     float2 gv[NCH], xh[NCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      gv[k] = __ldg(reinterpret_cast<const float2*>(gr + 64 * k + 2 * lane));
+      gv[k] = load2(gr + 64 * k + 2 * lane);
       const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + 64 * k + 2 * lane));
       xh[k] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
       dga[k].x += gv[k].x * xh[k].x; dga[k].y += gv[k].y * xh[k].y;
@@ -395,6 +400,68 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
     default: return set_error("ln_bwd: unsupported C=%d", C);
   }
 #undef CRF_LNB
+  CRF_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+// Stand-alone LayerNorm over contiguous (T, C) fp32 rows (the final norm_crf of a decoder stage,
+// newcrf_layers.py:430-431): y fp32 or bf16, stats (mean, rstd) for the backward.
+int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                         float* stats, int T, int C, cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "layernorm_fwd: C=%d must be a multiple of 64 in [64,1024]", C);
+  CRF_CHECK(y_dtype == CRF_DT_F32 || y_dtype == CRF_DT_BF16, "layernorm_fwd: unsupported output dtype %d", y_dtype);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int blocks = (T + 7) / 8;
+  const int cap = num_sms(dev) * 16;
+  if (blocks > cap) blocks = cap;
+  KernelTimer tm(st, 0.0, static_cast<double>(T) * C * (4 + (y_dtype == CRF_DT_F32 ? 4 : 2)), "layernorm_fwd_T%d_C%d", T, C);
+#define CRF_LNS(NCH)                                                                                                   \
+  case NCH:                                                                                                            \
+    if (y_dtype == CRF_DT_F32)                                                                                         \
+      ln_fwd_rows_kernel<float, NCH, true, float><<<blocks, 256, 0, st>>>(x, 0, C, T, T, gamma, beta, eps,             \
+                                                                            reinterpret_cast<float*>(y), stats, nullptr); \
+    else                                                                                                               \
+      ln_fwd_rows_kernel<float, NCH, true, __nv_bfloat16><<<blocks, 256, 0, st>>>(                                     \
+          x, 0, C, T, T, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), stats, nullptr);                       \
+    break;
+  switch (C / 64) {
+    CRF_LNS(1) CRF_LNS(2) CRF_LNS(3) CRF_LNS(4) CRF_LNS(5) CRF_LNS(6) CRF_LNS(7) CRF_LNS(8) CRF_LNS(9) CRF_LNS(10)
+    CRF_LNS(11) CRF_LNS(12) CRF_LNS(13) CRF_LNS(14) CRF_LNS(15) CRF_LNS(16)
+    default: return set_error("layernorm_fwd: unsupported C=%d", C);
+  }
+#undef CRF_LNS
+  CRF_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                         float* dgamma, float* dbeta, int T, int C, cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 64 in [64,1024]", C);
+  CRF_CHECK(g_dtype == CRF_DT_F32 || g_dtype == CRF_DT_BF16, "layernorm_bwd: unsupported gradient dtype %d", g_dtype);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int blocks = (T + 7) / 8;
+  const int cap = num_sms(dev) * 8;
+  if (blocks > cap) blocks = cap;
+  KernelTimer tm(st, 0.0, static_cast<double>(T) * C * (8 + (g_dtype == CRF_DT_F32 ? 4 : 2)), "layernorm_bwd_T%d_C%d", T, C);
+#define CRF_LNSB(NCH)                                                                                                  \
+  case NCH:                                                                                                            \
+    if (g_dtype == CRF_DT_F32)                                                                                         \
+      ln_bwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), x, stats, gamma, nullptr,   \
+                                                        dx, nullptr, dgamma, dbeta, T);                                \
+    else                                                                                                               \
+      ln_bwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), x, stats,    \
+                                                                gamma, nullptr, dx, nullptr, dgamma, dbeta, T);        \
+    break;
+  switch (C / 64) {
+    CRF_LNSB(1) CRF_LNSB(2) CRF_LNSB(3) CRF_LNSB(4) CRF_LNSB(5) CRF_LNSB(6) CRF_LNSB(7) CRF_LNSB(8) CRF_LNSB(9)
+    CRF_LNSB(10) CRF_LNSB(11) CRF_LNSB(12) CRF_LNSB(13) CRF_LNSB(14) CRF_LNSB(15) CRF_LNSB(16)
+    default: return set_error("layernorm_bwd: unsupported C=%d", C);
+  }
+#undef CRF_LNSB
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

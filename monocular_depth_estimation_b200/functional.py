@@ -84,7 +84,13 @@ class _CRFBlockFn(torch.autograd.Function):
         ws = torch.empty(ws_bwd, dtype=torch.uint8, device=dev)
         dx = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
         dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
-        grads = [torch.zeros_like(p) for p in params]
+        # one zero-filled buffer, 13 views (256-byte aligned: the kernels store with 16-byte vectors and TMA)
+        offs, o = [], 0
+        for p in params:
+            offs.append(o)
+            o += (p.numel() + 63) // 64 * 64
+        flat = torch.zeros(o, dtype=torch.float32, device=dev)
+        grads = [flat[a:a + p.numel()].view(p.shape) for a, p in zip(offs, params)]
         gs = L.BlockGrads()
         for name, t in zip(L.PARAM_NAMES, grads):
             setattr(gs, name, t.data_ptr())
@@ -116,6 +122,49 @@ def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None
     if qk_scale is None:
         qk_scale = (Cd // num_heads) ** -0.5
     return _CRFBlockFn.apply(x, v, v_bf16, H, W, num_heads, window, shift, float(qk_scale), float(eps), *params)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """LayerNorm over the last dim of contiguous fp32 token rows (the stage-closing `norm_crf`,
+    /root/reference/src/newcrf_layers.py:430-431) on the library's row kernels; output fp32, or bf16 when asked."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_bf16):
+        Cd = x.shape[-1]
+        xd = x.detach().contiguous()
+        T, dev = xd.numel() // Cd, xd.device
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        y = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        stats = torch.empty(T, 2, dtype=torch.float32, device=dev)
+        L.check(L.lib().crf_layernorm_fwd(xd.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps), y.data_ptr(),
+                                          L.CRF_DT_BF16 if out_bf16 else L.CRF_DT_F32, stats.data_ptr(), T, Cd,
+                                          dev.index, _stream_ptr(dev)), "crf_layernorm_fwd")
+        ctx.save_for_backward(xd, stats, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xd, stats, w = ctx.saved_tensors
+        Cd = xd.shape[-1]
+        T, dev = xd.numel() // Cd, xd.device
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        g = g.contiguous()
+        dx = torch.empty_like(xd)
+        dwb = torch.zeros(2, Cd, dtype=torch.float32, device=dev)
+        L.check(L.lib().crf_layernorm_bwd(g.data_ptr(), L.CRF_DT_BF16 if g.dtype == torch.bfloat16 else L.CRF_DT_F32,
+                                          xd.data_ptr(), stats.data_ptr(), w.data_ptr(), dx.data_ptr(),
+                                          dwb[0].data_ptr(), dwb[1].data_ptr(), T, Cd, dev.index, _stream_ptr(dev)),
+                "crf_layernorm_bwd")
+        return dx, dwb[0], dwb[1], None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
+    """nn.LayerNorm(C)(x) for fp32 CUDA x (..., C), C a multiple of 64 up to 1024.  out_dtype: torch.float32 (default)
+    or torch.bfloat16 (what a following autocast convolution would cast to anyway)."""
+    if not x.is_cuda:
+        raise RuntimeError("monocular_depth_estimation_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    return _LayerNormFn.apply(x.float(), weight, bias, float(eps), out_dtype == torch.bfloat16)
 
 
 class _WindowAttentionFn(torch.autograd.Function):

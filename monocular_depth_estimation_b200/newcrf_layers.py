@@ -184,7 +184,15 @@ class NewCRF(nn.Module):
         tokens = x.flatten(2).transpose(1, 2)      # (B, H*W, C) view of NCHW -- the kernel reads it strided
         v_hwc = v.permute(0, 2, 3, 1)              # (B, H, W, C) view of NCHW
         y = self.crf_layer(tokens, v_hwc, Wh, Ww)[0]
-        y = self.norm_crf(y)
+        if (y.is_cuda and type(self.norm_crf) is nn.LayerNorm and self.norm_crf.elementwise_affine
+                and self.embed_dim % 64 == 0 and self.embed_dim <= 1024):
+            # library row kernel; under bf16 autocast it emits bf16 directly (the next consumer is a convolution that
+            # would cast the fp32 result anyway -- same values, one pass less)
+            bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+            y = CF.layer_norm(y, self.norm_crf.weight, self.norm_crf.bias, self.norm_crf.eps,
+                              out_dtype=torch.bfloat16 if bf16 else torch.float32)
+        else:
+            y = self.norm_crf(y)
         out = y.view(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2)
         if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
             return out  # channels-last pipeline: the token-major result already IS NHWC memory, no copy needed

@@ -169,6 +169,34 @@ def test_ln_bwd(C):
     _check(dbeta, beta.grad, 1e-4, "ln_bwd.dbeta")
 
 
+@pytest.mark.parametrize("C", [64, 128, 256, 1024])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_layer_norm_standalone(C, out_bf16):
+    """functional.layer_norm (the stage-closing norm_crf, newcrf_layers.py:430-431) vs torch's fp32 LayerNorm:
+    forward, dx, dgamma, dbeta; fp32 output within 1e-5, bf16 output / bf16 incoming gradient within 2e-2 (bf16 I/O)."""
+    from monocular_depth_estimation_b200 import functional as CF
+    torch.manual_seed(C + int(out_bf16))
+    dev = torch.device("cuda:0")
+    B, T = 3, 331                                   # odd row count: exercises the grid-stride tail
+    x = (torch.randn(B, T, C, device=dev) * 1.7 + 0.3).requires_grad_(True)
+    w = (1 + 0.2 * torch.randn(C, device=dev)).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device=dev)).requires_grad_(True)
+    y = CF.layer_norm(x, w, b, 1e-5, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    assert y.dtype == (torch.bfloat16 if out_bf16 else torch.float32) and y.shape == x.shape
+    gy = torch.randn(B, T, C, device=dev)
+    if out_bf16:
+        gy = gy.to(torch.bfloat16)
+    y.backward(gy)
+    xr, wr, br = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    yr = F.layer_norm(xr, (C,), wr, br, 1e-5)
+    yr.backward(gy.float())
+    tol = 2e-2 if out_bf16 else 1e-5
+    _check(y.float(), yr, tol, "layer_norm y")
+    _check(x.grad, xr.grad, 2e-5 if not out_bf16 else 2e-2, "layer_norm dx")
+    _check(w.grad, wr.grad, 1e-4, "layer_norm dgamma")
+    _check(b.grad, br.grad, 1e-4, "layer_norm dbeta")
+
+
 def test_colsum_cast_convert():
     ops = _ops()
     gq = _rand_bf16(1234, 384, seed=11)
