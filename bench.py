@@ -392,6 +392,41 @@ def run_ours(args):
         with open(args.breakdown, "w") as f:
             json.dump(breakdown, f, indent=1)
 
+    # BASELINE.json's metric also names the CRF block itself: windows/s of one CRFBlock forward+backward at the four
+    # decoder scales of this workload (shifted windows), with the algorithmic tensor work of SURVEY.md 8(d)
+    # (22*49*C^2 + 4*49^2*C flops per window forward, x3 with backward) against the measured bf16 peak, and the
+    # attention-core kernels' algorithmic HBM rate (8 resp. 16 bytes per token-channel) against the measured HBM peak.
+    crf_blocks = None
+    if world == 1:
+        from monocular_depth_estimation_b200 import CRFBlock
+        crf_blocks = []
+        for scale, Cd, nH in ((4, 128, 4), (8, 256, 8), (16, 512, 16), (32, 1024, 32)):
+            Hs, Ws = H // scale, W // scale
+            blk = CRFBlock(Cd, nH, Cd, shift_size=3).to(device)
+            blk.H, blk.W = Hs, Ws
+            xb = torch.randn(B, Hs * Ws, Cd, device=device, requires_grad=True)
+            vb = torch.randn(B, Hs, Ws, Cd, device=device, requires_grad=True)
+            gy = torch.randn(B, Hs * Ws, Cd, device=device)
+
+            def blk_step():
+                blk(xb, vb, None).backward(gy)
+                xb.grad = vb.grad = None
+            for _ in range(3):
+                blk_step()
+            ms_b = timed(blk_step, 10) / 10
+            nwin = B * (-(-Hs // 7)) * (-(-Ws // 7))
+            fl = 3.0 * nwin * (22 * 49 * Cd * Cd + 4 * 49 * 49 * Cd)
+            ent = {"stage": f"1/{scale}", "H": Hs, "W": Ws, "C": Cd, "heads": nH, "windows": nwin,
+                   "ms_fwd_bwd": ms_b, "windows_per_s": nwin / (ms_b * 1e-3), "algorithmic_tflops": fl / (ms_b * 1e-3) / 1e12,
+                   "frac_of_bf16_peak": fl / (ms_b * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
+            for k in kernels:
+                for tag in ("attn_fwd", "attn_bwd"):
+                    if k["kernel"] == f"{tag}_B{B}_{Hs}x{Ws}_C{Cd}_s3" and k["total_ms"] > 0:
+                        us = k["total_ms"] / k["launches"] * 1e3
+                        ent[tag] = {"avg_us": us, "gbs": k["bytes"] / us / 1e3, "frac_of_hbm_peak": k["bytes"] / us / 1e3 / peaks["hbm_gbs"],
+                                    "tensor_tflops": k["flops"] / us / 1e6}
+            crf_blocks.append(ent)
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_run(args.ref_batch, H, W, steps=2, warmup=1)
@@ -417,6 +452,8 @@ def run_ours(args):
         "roofline": roof,
         "kernel_breakdown": breakdown[:8],
     }
+    if crf_blocks is not None:
+        line["crf_blocks"] = crf_blocks
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)

@@ -20,7 +20,9 @@ cap() {  # name, kernel regex, run_kernel args...
       python tools/run_kernel.py "$@" --iters 1 > $O/ncu_${name}_$TAG.log 2>&1
   echo "$name rc=$?"
 }
-cap gemm_fc1 gemm_persistent gemm --stage 0
+cap gemm_fc1 gemm_persistent gemms --stage 0 --only fc1+gelu
+cap gemm_dfc2 gemm_persistent gemms --stage 0 --only "d_fc2*gelu'"
+cap gemm_fc1_s3 gemm_persistent gemms --stage 3 --only fc1+gelu
 cap attn_fwd attn_fwd attn --stage 0
 cap attn_bwd attn_bwd attn --stage 0
 tail -n 2 $O/tests_$TAG.log; head -c 600 $O/bench_$TAG.json; echo

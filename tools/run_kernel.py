@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shift", type=int, default=3)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--only", default="", help="gemms: run only the shape with this label (e.g. \"d_fc2*gelu'\")")
     a = ap.parse_args()
     H, W, C, nH = STAGES[a.stage]
     B, dev = a.batch, torch.device("cuda:0")
@@ -68,6 +69,8 @@ def main():
                   ("d_fc2*gelu'", T, 4 * C, C, 1, L.EPI_MUL_DGELU), ("d_fc1", T, C, 4 * C, 1, L.EPI_STORE_F32),
                   ("d_proj", T, C, C, 1, L.EPI_STORE_BF16), ("d_qk", T, C, 2 * C, 1, L.EPI_STORE_F32)]
         for name, M, N, K, bmaj, epi in shapes:
+            if a.only and name != a.only:
+                continue
             A = torch.randn(M, K, device=dev).to(torch.bfloat16)
             Wt = (torch.randn(K, N, device=dev) if bmaj else torch.randn(N, K, device=dev)).to(torch.bfloat16)
             f32 = epi in (L.EPI_STORE_F32, L.EPI_BIAS_RES_F32)
