@@ -375,12 +375,12 @@ def run_ours(args):
                  "algorithmic_flops_per_launch": top["flops"], "algorithmic_bytes_per_launch": top["bytes"],
                  "achieved_tflops": tf, "achieved_gbs": gbs,
                  "peak_source": peaks["source"] + " (bf16 peak: sustained figure, kernel timed inside the step)",
-                 "share_of_step": top["total_ms"] / ms_probe, "share_of_crf_kernel_time": top["total_ms"] / tot,
+                 "share_of_step": top["total_ms"] / ms, "share_of_crf_kernel_time": top["total_ms"] / tot,
                  "crf_kernel_ms_per_step": tot / args.steps, "step_ms_with_events": ms_probe / args.steps,
                  "function_aggregate": {"launches": fam["launches"], "ms_per_step": fam["ms"] / args.steps,
-                                        "share_of_step": fam["ms"] / ms_probe,
+                                        "share_of_step": fam["ms"] / ms,
                                         "tflops": fam["flops"] / fam_s / 1e12, "gbs": fam["bytes"] / fam_s / 1e9},
-                 "families": {n: {"ms_per_step": f["ms"] / args.steps, "share_of_step": f["ms"] / ms_probe,
+                 "families": {n: {"ms_per_step": f["ms"] / args.steps, "share_of_step": f["ms"] / ms,
                                   "tflops": f["flops"] / (f["ms"] * 1e-3) / 1e12, "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9}
                               for n, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"])}})
     breakdown = [{"kernel": k["kernel"], "launches": k["launches"], "ms_per_step": k["total_ms"] / args.steps,

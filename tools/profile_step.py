@@ -42,8 +42,14 @@ def main():
         f.write(f"GPU kernel time per step: {tot:.3f} ms over {sum(r[2] for r in rows):.0f} launches\n")
         for k, ms, n in rows[:70]:
             f.write(f"{ms:9.3f} ms {n:7.1f}x  {k[:150]}\n")
-        f.write("\n" + ka.table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=60))
-    print(open(a.out).read()[:6000])
+        # GPU time attributed to framework-level ops (children included): where the stock-PyTorch glue spends it
+        ops = [(e.key, e.device_time_total / 1e3 / a.steps, e.count / a.steps) for e in ka
+               if e.device_type != torch.autograd.DeviceType.CUDA and e.device_time_total > 0]
+        ops.sort(key=lambda r: -r[1])
+        f.write("\nGPU ms per step by operator (inclusive)\n")
+        for k, ms, n in ops[:60]:
+            f.write(f"{ms:9.3f} ms {n:7.1f}x  {k[:110]}\n")
+    print(open(a.out).read()[-7000:])
 
 
 if __name__ == "__main__":
