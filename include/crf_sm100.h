@@ -188,6 +188,17 @@ int crf_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
                       float* stats, int T, int C, int device, void* stream);
 int crf_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
                       float* dgamma, float* dbeta, int T, int C, int device, void* stream);
+/* The training loop's loss, 1.0 * SSIM + 0.1 * L1 (replaces /root/reference/src/train.py:94-100 with the SSIM module of
+ * /root/reference/src/loss.py:57-88: reflection pad 1, 3x3 average pools, clamp((1 - n/d) / 2, 0, 1), mean).
+ *   pred f32 or bf16 (n_img, H, W) contiguous (n_img = batch x channels), target f32, H, W >= 2.
+ *   Forward ADDS to sums[0] the sum of the SSIM values and to sums[1] the sum of |pred - target| (caller zeroes them;
+ *   loss = (sums[0] + 0.1 * sums[1]) / (n_img * H * W)); if G != NULL it also writes the three f32 maps
+ *   (3, n_img, H, W) the backward needs.  Backward: dpred (dtype of pred) = *grad_loss * dloss/dpred, grad_loss a
+ *   device scalar. */
+int crf_depth_loss_fwd(const void* pred, int pred_dtype, const float* target, int n_img, int H, int W, float* sums,
+                       float* G, int device, void* stream);
+int crf_depth_loss_bwd(const void* pred, int pred_dtype, const float* target, const float* G, const float* grad_loss,
+                       int n_img, int H, int W, void* dpred, int device, void* stream);
 /* out[n] += sum_t g[t, n], g bf16 (T, N) */
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
 /* f32 -> bf16 contiguous */

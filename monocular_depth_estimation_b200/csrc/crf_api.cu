@@ -313,6 +313,21 @@ int crf_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* s
   CRF_CHECK(guard.ok, "cannot select device %d", device);
   return launch_layernorm_bwd(g, g_dtype, x, stats, gamma, dx, dgamma, dbeta, T, C, static_cast<cudaStream_t>(stream));
 }
+int crf_depth_loss_fwd(const void* pred, int pred_dtype, const float* target, int n_img, int H, int W, float* sums,
+                       float* G, int device, void* stream) {
+  CRF_CHECK(pred && target && sums, "crf_depth_loss_fwd: null pointer");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_depth_loss_fwd(pred, pred_dtype, target, n_img, H, W, sums, G, static_cast<cudaStream_t>(stream));
+}
+int crf_depth_loss_bwd(const void* pred, int pred_dtype, const float* target, const float* G, const float* grad_loss,
+                       int n_img, int H, int W, void* dpred, int device, void* stream) {
+  CRF_CHECK(pred && target && G && grad_loss && dpred, "crf_depth_loss_bwd: null pointer");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_depth_loss_bwd(pred, pred_dtype, target, G, grad_loss, n_img, H, W, dpred,
+                               static_cast<cudaStream_t>(stream));
+}
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream) {
   DeviceGuard guard(device);
   CRF_CHECK(guard.ok, "cannot select device %d", device);

@@ -80,6 +80,10 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
                          float* stats, int T, int C, cudaStream_t st);
 int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
                          float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
+int launch_depth_loss_fwd(const void* pred, int pred_dtype, const float* tgt, int n_img, int H, int W, float* sums,
+                          float* G, cudaStream_t st);
+int launch_depth_loss_bwd(const void* pred, int pred_dtype, const float* tgt, const float* G, const float* gout,
+                          int n_img, int H, int W, void* dpred, cudaStream_t st);
 int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st);
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
 int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long long n[4], cudaStream_t st);

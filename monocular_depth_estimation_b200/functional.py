@@ -167,6 +167,50 @@ def layer_norm(x, weight, bias, eps=1e-5, out_dtype=None):
     return _LayerNormFn.apply(x.float(), weight, bias, float(eps), out_dtype == torch.bfloat16)
 
 
+class _DepthLossFn(torch.autograd.Function):
+    """loss = SSIM(pred, target) + 0.1 * L1(pred, target) of the reference loop (src/train.py:94-100, src/loss.py:57-88)
+    in one forward and one backward kernel; pred fp32 or bf16 (B, C, H, W), target fp32, no gradient for target."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        p = pred.detach().contiguous()
+        t = target.detach().float().contiguous()
+        H, W = p.shape[-2:]
+        n_img, dev = p.numel() // (H * W), p.device
+        need = ctx.needs_input_grad[0]
+        sums = torch.zeros(2, dtype=torch.float32, device=dev)
+        G = torch.empty(3, n_img, H, W, dtype=torch.float32, device=dev) if need else None
+        dt = L.CRF_DT_BF16 if p.dtype == torch.bfloat16 else L.CRF_DT_F32
+        L.check(L.lib().crf_depth_loss_fwd(p.data_ptr(), dt, t.data_ptr(), n_img, H, W, sums.data_ptr(),
+                                           None if G is None else G.data_ptr(), dev.index, _stream_ptr(dev)),
+                "crf_depth_loss_fwd")
+        if need:
+            ctx.save_for_backward(p, t, G)
+        return (sums[0] + 0.1 * sums[1]) / float(p.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t, G = ctx.saved_tensors
+        H, W = p.shape[-2:]
+        n_img, dev = p.numel() // (H * W), p.device
+        g = g.detach().float().contiguous()
+        dp = torch.empty_like(p)
+        dt = L.CRF_DT_BF16 if p.dtype == torch.bfloat16 else L.CRF_DT_F32
+        L.check(L.lib().crf_depth_loss_bwd(p.data_ptr(), dt, t.data_ptr(), G.data_ptr(), g.data_ptr(), n_img, H, W,
+                                           dp.data_ptr(), dev.index, _stream_ptr(dev)), "crf_depth_loss_bwd")
+        return dp, None
+
+
+def depth_loss(pred, target):
+    """1.0 * SSIM + 0.1 * L1 (src/train.py:94-100) for CUDA tensors (B, C, H, W), H, W >= 2."""
+    if not pred.is_cuda:
+        raise RuntimeError("monocular_depth_estimation_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    assert pred.shape == target.shape and pred.dim() == 4, "depth_loss expects pred and target of one (B, C, H, W) shape"
+    if pred.dtype not in (torch.float32, torch.bfloat16):
+        pred = pred.float()
+    return _DepthLossFn.apply(pred, target)
+
+
 class _WindowAttentionFn(torch.autograd.Function):
     """Stand-alone WindowAttention.forward (newcrf_layers.py:110-149) on already-partitioned windows, built from the
     stage-level entry points: qk GEMM -> attention core (each window = a 7x7 image, no pad, no shift) -> proj GEMM."""

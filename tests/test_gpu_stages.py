@@ -197,6 +197,32 @@ def test_layer_norm_standalone(C, out_bf16):
     _check(b.grad, br.grad, 1e-4, "layer_norm dbeta")
 
 
+@pytest.mark.parametrize("shape", [(2, 1, 37, 53), (1, 1, 2, 2), (3, 1, 3, 5), (2, 1, 120, 160)])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_depth_loss(shape, bf16):
+    """functional.depth_loss (SSIM + 0.1 L1, train.py:94-100 / loss.py:57-88) vs the oracle's composition of torch
+    ops evaluated in fp64 on the same (bf16-rounded) prediction: loss value and d loss / d pred."""
+    from monocular_depth_estimation_b200 import functional as CF
+    from oracle import model_oracle as MO
+    torch.manual_seed(sum(shape) + int(bf16))
+    dev = torch.device("cuda:0")
+    pred = torch.rand(shape, device=dev)
+    tgt = (0.5 * pred + 0.5 * torch.rand(shape, device=dev)).clamp(0, 1)
+    tgt[..., : shape[-1] // 2] = pred[..., : shape[-1] // 2]      # a region with SSIM ~ 1 (clamp boundary)
+    if bf16:
+        pred = pred.to(torch.bfloat16)
+    pred.requires_grad_(True)
+    loss = CF.depth_loss(pred, tgt)
+    loss.backward()
+    pr = pred.detach().double().cpu().requires_grad_(True)
+    lr = MO.ssim_l1_loss(pr, tgt.double().cpu())
+    lr.backward()
+    assert abs(float(loss) - float(lr)) < 2e-5 * max(1.0, abs(float(lr))), (float(loss), float(lr))
+    assert pred.grad.dtype == pred.dtype
+    _check(pred.grad.float().reshape(-1, shape[-1]), pr.grad.float().reshape(-1, shape[-1]), 1e-2 if bf16 else 2e-4,
+           "depth_loss d pred")
+
+
 def test_colsum_cast_convert():
     ops = _ops()
     gq = _rand_bf16(1234, 384, seed=11)

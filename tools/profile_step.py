@@ -29,7 +29,7 @@ def main():
         train_step(model, opt, img, dep)
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         for _ in range(a.steps):
             train_step(model, opt, img, dep)
         torch.cuda.synchronize()
@@ -49,7 +49,16 @@ def main():
         f.write("\nGPU ms per step by operator (inclusive)\n")
         for k, ms, n in ops[:60]:
             f.write(f"{ms:9.3f} ms {n:7.1f}x  {k[:110]}\n")
-    print(open(a.out).read()[-7000:])
+    with open(a.out, "a") as f:
+        f.write("\nLargest layout / dtype copies by input shape (GPU ms per step)\n")
+        kas = prof.key_averages(group_by_input_shape=True)
+        rows = [(e.key, str(e.input_shapes)[:90], e.device_time_total / 1e3 / a.steps, e.count / a.steps) for e in kas
+                if e.key in ("aten::copy_", "aten::contiguous", "aten::clone", "aten::_to_copy", "aten::add_", "aten::sum",
+                             "aten::pixel_shuffle", "aten::pixel_unshuffle", "aten::mul", "aten::add")]
+        rows.sort(key=lambda r: -r[2])
+        for k, shp, ms, n in rows[:45]:
+            f.write(f"{ms:9.3f} ms {n:6.1f}x  {k:22s} {shp}\n")
+    print(open(a.out).read()[-6500:])
 
 
 if __name__ == "__main__":
