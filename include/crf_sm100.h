@@ -199,6 +199,13 @@ int crf_depth_loss_fwd(const void* pred, int pred_dtype, const float* target, in
                        float* G, int device, void* stream);
 int crf_depth_loss_bwd(const void* pred, int pred_dtype, const float* target, const float* G, const float* grad_loss,
                        int n_img, int H, int W, void* dpred, int device, void* stream);
+/* PixelShuffle(2) between decoder stages (replaces nn.PixelShuffle(2),
+ * /root/reference/src/model_mobileV3_large_newCRFs.py:116-120) on channels-last memory, f32 or bf16:
+ *   inverse == 0: src (B, H, W, C) -> dst (B, 2H, 2W, C/4), dst[b, 2h+i, 2w+j, c] = src[b, h, w, 4c + 2i + j]
+ *   inverse != 0: src (B, 2H, 2W, C/4) -> dst (B, H, W, C)   (pixel_unshuffle: the backward)
+ * B, H, W, C always describe the (B, H, W, C) side; C % 4 == 0. */
+int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, int inverse, int device,
+                           void* stream);
 /* out[n] += sum_t g[t, n], g bf16 (T, N) */
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
 /* f32 -> bf16 contiguous */

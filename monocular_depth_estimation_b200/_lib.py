@@ -26,7 +26,7 @@ EPI_SPLITK_F32 = 5
 EXPORTED_SYMBOLS = (
     "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_timing_enable", "crf_timing_report", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
     "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_gemm_workspace_bytes", "crf_ln_fwd", "crf_ln_bwd",
-    "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd",
+    "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd", "crf_pixel_shuffle_nhwc",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd",
 )
 
@@ -97,6 +97,7 @@ def _declare(lib):
     lib.crf_layernorm_bwd.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.crf_depth_loss_fwd.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp]
     lib.crf_depth_loss_bwd.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, vp, i32, vp]
+    lib.crf_pixel_shuffle_nhwc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_colsum_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.crf_cast_bf16.argtypes = [vp, vp, i64, i32, vp]
     lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp]

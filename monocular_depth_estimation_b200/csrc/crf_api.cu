@@ -328,6 +328,13 @@ int crf_depth_loss_bwd(const void* pred, int pred_dtype, const float* target, co
   return launch_depth_loss_bwd(pred, pred_dtype, target, G, grad_loss, n_img, H, W, dpred,
                                static_cast<cudaStream_t>(stream));
 }
+int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, int inverse, int device,
+                           void* stream) {
+  CRF_CHECK(src && dst, "crf_pixel_shuffle_nhwc: null pointer");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_pixel_shuffle_nhwc(src, dst, dtype, B, H, W, C, inverse, static_cast<cudaStream_t>(stream));
+}
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream) {
   DeviceGuard guard(device);
   CRF_CHECK(guard.ok, "cannot select device %d", device);

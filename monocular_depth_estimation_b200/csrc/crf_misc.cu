@@ -303,6 +303,43 @@ __global__ void shift_mask_kernel(float* __restrict__ mask, WindowGeom gm) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PixelShuffle(2) between decoder stages (model_mobileV3_large_newCRFs.py:116-120) on channels-last memory:
+//   dst[b, 2h+i, 2w+j, c'] = src[b, h, w, 4c' + 2i + j]        src (B, H, W, C), dst (B, 2H, 2W, C/4)
+// One warp per source pixel: a lane loads the four channels of one output channel c' (one 8- or 16-byte load) and
+// writes them to the four output pixels; INVERSE runs the same index map the other way (the backward).
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(256)
+pixel_shuffle_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int H, int W, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  const int Cq = C >> 2;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); p < npix;
+       p += static_cast<int64_t>(gridDim.x) * 8) {
+    const int w = static_cast<int>(p % W);
+    const int64_t bh = p / W;  // b * H + h
+    const T* big = (INVERSE ? dst : src) + p * C;                       // the (B, H, W, C) side
+    const T* small00 = (INVERSE ? src : dst) + ((bh * 2) * (2 * W) + 2 * w) * Cq;   // output pixel (2h, 2w)
+    const int64_t row = static_cast<int64_t>(2 * W) * Cq;               // one output row down
+    for (int cq = lane; cq < Cq; cq += 32) {
+      T v[4];
+      if (!INVERSE) {
+        if (sizeof(T) == 2) *reinterpret_cast<uint2*>(v) = __ldg(reinterpret_cast<const uint2*>(big + 4 * cq));
+        else *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(big + 4 * cq));
+        T* o = const_cast<T*>(small00) + cq;
+        o[0] = v[0]; o[Cq] = v[1]; o[row] = v[2]; o[row + Cq] = v[3];
+      } else {
+        const T* o = small00 + cq;
+        v[0] = o[0]; v[1] = o[Cq]; v[2] = o[row]; v[3] = o[row + Cq];
+        T* d = const_cast<T*>(big) + 4 * cq;
+        if (sizeof(T) == 2) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(v);
+        else *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+  }
+}
+
 template <typename TIn>
 int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C, const float* gamma,
                     const float* beta, float eps, void* xn, float* stats, float* x_copy, cudaStream_t st) {
@@ -462,6 +499,31 @@ int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float
     default: return set_error("layernorm_bwd: unsupported C=%d", C);
   }
 #undef CRF_LNSB
+  CRF_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, int inverse,
+                              cudaStream_t st) {
+  CRF_CHECK(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "pixel_shuffle_nhwc: bad shape (B=%d H=%d W=%d C=%d)", B, H, W, C);
+  CRF_CHECK(dtype == CRF_DT_F32 || dtype == CRF_DT_BF16, "pixel_shuffle_nhwc: unsupported dtype %d", dtype);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  int64_t blocks = (npix + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(num_sms(dev)) * 16;
+  if (blocks > cap) blocks = cap;
+  const int esz = dtype == CRF_DT_F32 ? 4 : 2;
+  KernelTimer tm(st, 0.0, 2.0 * npix * C * esz, "pixel_%sshuffle_B%d_%dx%d_C%d", inverse ? "un" : "", B, H, W, C);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  if (dtype == CRF_DT_F32) {
+    if (inverse) pixel_shuffle_nhwc_kernel<float, true><<<nb, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), B, H, W, C);
+    else pixel_shuffle_nhwc_kernel<float, false><<<nb, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), B, H, W, C);
+  } else {
+    if (inverse) pixel_shuffle_nhwc_kernel<__nv_bfloat16, true><<<nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C);
+    else pixel_shuffle_nhwc_kernel<__nv_bfloat16, false><<<nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C);
+  }
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

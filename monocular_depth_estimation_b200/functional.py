@@ -211,6 +211,42 @@ def depth_loss(pred, target):
     return _DepthLossFn.apply(pred, target)
 
 
+class _PixelShuffleFn(torch.autograd.Function):
+    """nn.PixelShuffle(2) for channels-last CUDA tensors (model_mobileV3_large_newCRFs.py:116-120): one permutation
+    pass in NHWC memory each way instead of torch's NCHW shuffle plus a layout copy for the following convolution."""
+
+    @staticmethod
+    def _run(src, inverse):
+        if inverse:   # src logical (B, C/4, 2H, 2W) -> (B, C, H, W)
+            B, Cq, H2, W2 = src.shape
+            Cd, H, W = Cq * 4, H2 // 2, W2 // 2
+            out_shape = (B, Cd, H, W)
+        else:         # src logical (B, C, H, W) -> (B, C/4, 2H, 2W)
+            B, Cd, H, W = src.shape
+            out_shape = (B, Cd // 4, 2 * H, 2 * W)
+        dst = torch.empty(out_shape, dtype=src.dtype, device=src.device, memory_format=torch.channels_last)
+        dt = L.CRF_DT_BF16 if src.dtype == torch.bfloat16 else L.CRF_DT_F32
+        L.check(L.lib().crf_pixel_shuffle_nhwc(src.data_ptr(), dst.data_ptr(), dt, B, H, W, Cd, int(inverse),
+                                               src.device.index, _stream_ptr(src.device)), "crf_pixel_shuffle_nhwc")
+        return dst
+
+    @staticmethod
+    def forward(ctx, x):
+        return _PixelShuffleFn._run(x.detach(), False)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _PixelShuffleFn._run(g.contiguous(memory_format=torch.channels_last), True)
+
+
+def pixel_shuffle2(x):
+    """F.pixel_shuffle(x, 2); channels-last fp32 / bf16 CUDA tensors take the library's NHWC permutation kernel."""
+    if (x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype in (torch.float32, torch.bfloat16)
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        return _PixelShuffleFn.apply(x)
+    return torch.nn.functional.pixel_shuffle(x, 2)
+
+
 class _WindowAttentionFn(torch.autograd.Function):
     """Stand-alone WindowAttention.forward (newcrf_layers.py:110-149) on already-partitioned windows, built from the
     stage-level entry points: qk GEMM -> attention core (each window = a 7x7 image, no pad, no shift) -> proj GEMM."""

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .functional import pixel_shuffle2
 from .newcrf_layers import NewCRF
 
 CRF_DIMS = (128, 256, 512, 1024)      # embed dim per scale 1/4 .. 1/32
@@ -36,7 +37,7 @@ class Decoder(nn.Module):
         e = self.conv0(feats[ENC_TAPS[4]])
         for s in (3, 2, 1, 0):
             if s != 3:
-                e = F.pixel_shuffle(e, 2)
+                e = pixel_shuffle2(e)
             e = getattr(self, f"crf{s}")(feats[ENC_TAPS[s]], e)
         d = self.sigmoid(self.conv1(e))
         return F.interpolate(d, scale_factor=4, mode="bilinear", align_corners=False)

@@ -223,6 +223,23 @@ def test_depth_loss(shape, bf16):
            "depth_loss d pred")
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 6, 5), (1, 1024, 3, 4), (2, 12, 5, 7), (8, 256, 60, 80)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pixel_shuffle_nhwc_bit_exact(shape, dtype):
+    """functional.pixel_shuffle2 on channels-last tensors == F.pixel_shuffle(x, 2), forward and backward, bit-exact
+    (a pure permutation: model_mobileV3_large_newCRFs.py:116-120)."""
+    from monocular_depth_estimation_b200 import functional as CF
+    torch.manual_seed(sum(shape))
+    x = torch.randn(shape, device="cuda:0").to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = CF.pixel_shuffle2(x)
+    ref = F.pixel_shuffle(x.detach(), 2)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y, ref)
+    g = torch.randn_like(ref)
+    y.backward(g)
+    assert torch.equal(x.grad, F.pixel_unshuffle(g, 2))
+
+
 def test_colsum_cast_convert():
     ops = _ops()
     gq = _rand_bf16(1234, 384, seed=11)
