@@ -331,6 +331,33 @@ def test_attn_fwd(B, H, W, C, nH, shift):
     _check(lse[:, :, :49], ref_lse, 1e-4, "attn_fwd.lse")
 
 
+@pytest.mark.parametrize("B,H,W,C,nH,shift", [(8, 120, 160, 128, 4, 3), (8, 30, 40, 512, 16, 3), (2, 23, 17, 64, 2, 3)])
+def test_attn_repeatable(B, H, W, C, nH, shift):
+    """Race hunt for the asynchronous attention pipeline (hardware-made mbarrier arrivals, two MMA-issuing warps,
+    accumulator pre-load, transposed stores): every output that involves no floating-point atomics must be bit-identical
+    over repeated launches at the full config-2 shape, and untouched by other work running between the launches."""
+    ops = _ops()
+    T = B * H * W
+    qk = _rand_bf16(T, 2 * C, seed=31, scale=0.7)
+    vb = _rand_bf16(T, C, seed=32)
+    dout = _rand_bf16(T, C, seed=33)
+    qk_bias = torch.randn(2 * C, device=DEV) * 0.5
+    table = torch.randn(169, nH, device=DEV) * 0.5
+    d = ops.make_desc(B, H, W, C, nH, shift, device=torch.cuda.current_device())
+    scale = (C // nH) ** -0.5
+    o0, lse0 = ops.attn_fwd(d, qk, vb, qk_bias, scale, table)
+    dqk0, dv0, dt0, db0 = ops.attn_bwd(d, qk, vb, qk_bias, scale, table, lse0, dout)
+    junk = torch.empty(64 << 20, device=DEV)
+    for it in range(6):
+        junk.normal_()                                    # evict L2, perturb timing
+        o, lse = ops.attn_fwd(d, qk, vb, qk_bias, scale, table)
+        dqk, dv, dt, db = ops.attn_bwd(d, qk, vb, qk_bias, scale, table, lse, dout)
+        assert torch.equal(o, o0) and torch.equal(lse, lse0), f"forward differs on repeat {it}"
+        assert torch.equal(dqk, dqk0) and torch.equal(dv, dv0), f"backward differs on repeat {it}"
+        _check(dt, dt0, 1e-5, "d_table (atomics: order-dependent rounding only)")
+        _check(db, db0, 1e-5, "d_qk_bias (atomics: order-dependent rounding only)")
+
+
 @pytest.mark.parametrize("B,H,W,C,nH,shift", ATTN_CASES)
 def test_attn_bwd(B, H, W, C, nH, shift):
     ops = _ops()
