@@ -115,6 +115,32 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
                   const void* saved, float* dx, float* dv, int dv_accumulate, const crf_block_grads* g, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* --------------------------------------------------------------------------------------------------------
+ * Layer level: BasicCRFLayer.forward (newcrf_layers.py:323-363) -- `depth` blocks with shift 0, window/2, 0, ...
+ * that all read the same v -- optionally followed by the LayerNorm that closes a decoder stage (NewCRF.norm_crf,
+ * newcrf_layers.py:430-431), in ONE call each way.  Compared with `depth` crf_block_* calls this converts v once,
+ * hands the gradient between blocks in fp32 + bf16 without extra casts and accumulates dv inside the kernels.
+ *   d      : descriptor of the layer's input x / v (the shift field is ignored; blocks after the first read the
+ *            previous block's contiguous fp32 output)
+ *   y      : (B, H*W, C) contiguous, f32, or bf16 when out_dtype == CRF_DT_BF16 (needs the closing norm)
+ *   dy     : gradient of y in y's dtype; dx (B, H*W, C) f32; dv (B, H, W, C) f32 (overwritten)
+ *   g      : `depth` gradient structs (accumulated, +=); dnorm_w / dnorm_b accumulated, NULL without the norm
+ * ------------------------------------------------------------------------------------------------------ */
+#define CRF_MAX_DEPTH 8
+typedef struct crf_layer_args {
+  int32_t depth;
+  int32_t out_dtype;               /* CRF_DT_F32 or CRF_DT_BF16 */
+  const crf_block_params* params;  /* [depth] */
+  const float* norm_w;             /* closing LayerNorm weight (C) or NULL */
+  const float* norm_b;
+} crf_layer_args;
+int crf_layer_sizes(const crf_block_desc* d, int depth, int with_norm, size_t* saved_bytes, size_t* ws_bwd_bytes);
+int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, void* y, void* saved,
+                  void* stream);
+int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, const void* dy,
+                  const void* saved, float* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
+                  void* ws, size_t ws_bytes, void* stream);
+
 /* v (B,H,W,C), any strides, fp32/bf16 -> bf16 token-major (T, C) contiguous; done once per BasicCRFLayer
  * because both blocks read the same v (newcrf_layers.py:352-357). Uses the v_* fields of the descriptor. */
 int crf_convert_v(const crf_block_desc* d, const void* v, void* v_bf16, void* stream);

@@ -25,6 +25,7 @@ EPI_SPLITK_F32 = 5
 # every symbol include/crf_sm100.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
     "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_timing_enable", "crf_timing_report", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
+    "crf_layer_sizes", "crf_layer_fwd", "crf_layer_bwd",
     "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_gemm_workspace_bytes", "crf_ln_fwd", "crf_ln_bwd",
     "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd", "crf_pixel_shuffle_nhwc",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd",
@@ -52,6 +53,11 @@ class BlockParams(C.Structure):
 
 class BlockGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_NAMES]
+
+
+class LayerArgs(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("out_dtype", C.c_int32), ("params", C.POINTER(BlockParams)),
+                ("norm_w", C.c_void_p), ("norm_b", C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -85,6 +91,10 @@ def _declare(lib):
     lib.crf_block_bwd.argtypes = [C.POINTER(BlockDesc), C.POINTER(BlockParams), vp, vp, vp, vp, vp, vp, i32,
                                   C.POINTER(BlockGrads), vp, sz, vp]
     lib.crf_convert_v.argtypes = [C.POINTER(BlockDesc), vp, vp, vp]
+    lib.crf_layer_sizes.argtypes = [C.POINTER(BlockDesc), i32, i32, C.POINTER(sz), C.POINTER(sz)]
+    lib.crf_layer_fwd.argtypes = [C.POINTER(BlockDesc), C.POINTER(LayerArgs), vp, vp, vp, vp, vp]
+    lib.crf_layer_bwd.argtypes = [C.POINTER(BlockDesc), C.POINTER(LayerArgs), vp, vp, vp, vp, vp, vp,
+                                  C.POINTER(BlockGrads), vp, vp, vp, sz, vp]
     lib.crf_window_gather.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_window_scatter.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_shift_mask.argtypes = [vp, i32, i32, i32, i32, vp]

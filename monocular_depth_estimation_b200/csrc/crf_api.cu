@@ -152,9 +152,8 @@ int crf_convert_v(const crf_block_desc* d, const void* v, void* v_bf16, void* st
                                v_bf16, static_cast<cudaStream_t>(stream));
 }
 
-int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, float* y,
-                  void* saved, void* ws, size_t ws_bytes, void* stream) {
-  (void)ws; (void)ws_bytes;
+static int block_fwd_impl(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, float* y,
+                          void* saved, void* stream) {
   if (check_desc(d)) return 1;
   CRF_CHECK(p && x && v && y && saved, "crf_block_fwd: null pointer");
   DeviceGuard guard(d->device);
@@ -211,9 +210,10 @@ int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void
   return 0;
 }
 
-int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, const float* dy,
-                  const void* saved, float* dx, float* dv, int dv_accumulate, const crf_block_grads* g, void* ws,
-                  size_t ws_bytes, void* stream) {
+// dy_bf16: optional bf16 twin of dy (saves the cast); dx_bf16: optional bf16 twin of dx to write.
+static int block_bwd_impl(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v,
+                          const float* dy, const void* dy_bf16, const void* saved, float* dx, void* dx_bf16, float* dv,
+                          int dv_accumulate, const crf_block_grads* g, void* ws, size_t ws_bytes, void* stream) {
   if (check_desc(d)) return 1;
   CRF_CHECK(p && x && v && dy && saved && dx && dv && g && ws, "crf_block_bwd: null pointer");
   CRF_CHECK(d->training, "crf_block_bwd: forward was not run with training=1");
@@ -233,9 +233,13 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
   float* dx1 = reinterpret_cast<float*>(Wk + W.dx1);
 
   // ---- MLP ----
-  if (launch_cast_bf16(dy, Wk + W.dyb, static_cast<int64_t>(T) * C, st)) return 1;
-  if (gemm_dgrad(Wk + W.dyb, S + L.wb_fc2, T, 4 * C, C, CRF_EPI_MUL_DGELU, Wk + W.dhpre, S + L.pre, dev, st)) return 1;
-  if (gemm_wgrad(Wk + W.dyb, S + L.act, C, 4 * C, T, g->fc2_w, g->fc2_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
+  const void* dyb = dy_bf16;
+  if (dyb == nullptr) {
+    if (launch_cast_bf16(dy, Wk + W.dyb, static_cast<int64_t>(T) * C, st)) return 1;
+    dyb = Wk + W.dyb;
+  }
+  if (gemm_dgrad(dyb, S + L.wb_fc2, T, 4 * C, C, CRF_EPI_MUL_DGELU, Wk + W.dhpre, S + L.pre, dev, st)) return 1;
+  if (gemm_wgrad(dyb, S + L.act, C, 4 * C, T, g->fc2_w, g->fc2_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (gemm_dgrad(Wk + W.dhpre, S + L.wb_fc1, T, C, 4 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
   if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, g->fc1_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
   if (launch_ln_bwd(dxn, reinterpret_cast<const float*>(S + L.x1), reinterpret_cast<const float*>(S + L.stats2),
@@ -250,9 +254,173 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
     return 1;
   if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
   if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, g->qk_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, nullptr,
+  if (launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, dx_bf16,
                     g->norm1_w, g->norm1_b, T, C, st))
     return 1;
+  return 0;
+}
+
+int crf_block_fwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, float* y,
+                  void* saved, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  return block_fwd_impl(d, p, x, v, y, saved, stream);
+}
+
+int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, const float* dy,
+                  const void* saved, float* dx, float* dv, int dv_accumulate, const crf_block_grads* g, void* ws,
+                  size_t ws_bytes, void* stream) {
+  return block_bwd_impl(d, p, x, v, dy, nullptr, saved, dx, nullptr, dv, dv_accumulate, g, ws, ws_bytes, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Layer level: BasicCRFLayer.forward (newcrf_layers.py:323-363: `depth` blocks, shift 0 / window/2 alternating, the
+// same v for every block) plus, optionally, the LayerNorm that closes the decoder stage (NewCRF.norm_crf, :430-431).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct LayerLayout {
+  size_t vb, norm_stats, total;
+  size_t blk[CRF_MAX_DEPTH], yout[CRF_MAX_DEPTH];  // per block: its `saved` area and its fp32 output (T, C)
+};
+crf_block_desc block_desc_of(const crf_block_desc& d, int i) {
+  crf_block_desc b = d;
+  b.shift = (i % 2 == 0) ? 0 : d.window / 2;
+  b.v_preconverted = 1;
+  if (i > 0) {  // blocks after the first read the previous block's contiguous fp32 output
+    b.x_dtype = CRF_DT_F32;
+    b.x_stride_c = 1;
+    b.x_stride_t = d.C;
+    b.x_stride_b = static_cast<int64_t>(d.H) * d.W * d.C;
+  }
+  return b;
+}
+LayerLayout layer_layout(const crf_block_desc& d, int depth, int with_norm) {
+  LayerLayout L{};
+  const size_t T = static_cast<size_t>(d.B) * d.H * d.W, C = d.C;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
+  L.vb = take(T * C * 2);
+  for (int i = 0; i < depth; ++i) {
+    L.blk[i] = take(saved_layout(block_desc_of(d, i)).total);
+    // the last block's output is the caller's y unless a closing norm follows (then LN backward needs it)
+    L.yout[i] = (i + 1 < depth || with_norm) ? take(T * C * 4) : 0;
+  }
+  L.norm_stats = take(with_norm ? T * 2 * 4 : 0);
+  L.total = o;
+  return L;
+}
+struct LayerBwdLayout {
+  size_t blk, g_f32, g_bf16, mid_f32, mid_bf16, total;
+};
+LayerBwdLayout layer_bwd_layout(const crf_block_desc& d, int depth, int with_norm) {
+  LayerBwdLayout L{};
+  const size_t T = static_cast<size_t>(d.B) * d.H * d.W, C = d.C;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
+  L.blk = take(bwd_layout(block_desc_of(d, depth > 1 ? 1 : 0)).total);
+  L.g_f32 = take(with_norm ? T * C * 4 : 0);
+  L.g_bf16 = take(with_norm ? T * C * 2 : 0);
+  L.mid_f32 = take(depth > 1 ? 2 * T * C * 4 : 0);   // ping-pong buffers for the gradient between blocks
+  L.mid_bf16 = take(depth > 1 ? 2 * T * C * 2 : 0);
+  L.total = o;
+  return L;
+}
+int check_layer(const crf_block_desc* d, const crf_layer_args* a) {
+  if (check_desc(d)) return 1;
+  CRF_CHECK(a != nullptr && a->params != nullptr, "crf_layer: null arguments");
+  CRF_CHECK(a->depth >= 1 && a->depth <= CRF_MAX_DEPTH, "crf_layer: depth %d not in [1, %d]", a->depth, CRF_MAX_DEPTH);
+  CRF_CHECK((a->norm_w == nullptr) == (a->norm_b == nullptr), "crf_layer: norm_w and norm_b go together");
+  CRF_CHECK(a->out_dtype == CRF_DT_F32 || (a->out_dtype == CRF_DT_BF16 && a->norm_w != nullptr),
+            "crf_layer: bf16 output needs the closing LayerNorm");
+  return 0;
+}
+}  // namespace
+
+int crf_layer_sizes(const crf_block_desc* d, int depth, int with_norm, size_t* saved_bytes, size_t* ws_bwd_bytes) {
+  if (check_desc(d)) return 1;
+  CRF_CHECK(depth >= 1 && depth <= CRF_MAX_DEPTH, "crf_layer: depth %d not in [1, %d]", depth, CRF_MAX_DEPTH);
+  if (saved_bytes) *saved_bytes = layer_layout(*d, depth, with_norm).total;
+  if (ws_bwd_bytes) *ws_bwd_bytes = layer_bwd_layout(*d, depth, with_norm).total;
+  return 0;
+}
+
+int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, void* y, void* saved,
+                  void* stream) {
+  if (check_layer(d, a)) return 1;
+  CRF_CHECK(x && v && y && saved, "crf_layer_fwd: null pointer");
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  const int with_norm = a->norm_w != nullptr;
+  const LayerLayout L = layer_layout(*d, a->depth, with_norm);
+  uint8_t* S = static_cast<uint8_t*>(saved);
+  const int T = d->B * d->H * d->W;
+  crf_block_desc d0 = *d;
+  d0.v_preconverted = 0;
+  if (crf_convert_v(&d0, v, S + L.vb, stream)) return 1;
+  const void* xin = x;
+  for (int i = 0; i < a->depth; ++i) {
+    const crf_block_desc bd = block_desc_of(*d, i);
+    float* yo = (i + 1 == a->depth && !with_norm) ? static_cast<float*>(y) : reinterpret_cast<float*>(S + L.yout[i]);
+    if (block_fwd_impl(&bd, a->params + i, xin, S + L.vb, yo, S + L.blk[i], stream)) return 1;
+    xin = yo;
+  }
+  if (with_norm) {
+    if (launch_layernorm_fwd(static_cast<const float*>(xin), a->norm_w, a->norm_b, a->params[0].ln_eps, y, a->out_dtype,
+                             reinterpret_cast<float*>(S + L.norm_stats), T, d->C, static_cast<cudaStream_t>(stream)))
+      return 1;
+  }
+  return 0;
+}
+
+int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, const void* dy,
+                  const void* saved, float* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
+                  void* ws, size_t ws_bytes, void* stream) {
+  (void)v;
+  if (check_layer(d, a)) return 1;
+  CRF_CHECK(x && dy && saved && dx && dv && g && ws, "crf_layer_bwd: null pointer");
+  CRF_CHECK(d->training, "crf_layer_bwd: forward was not run with training=1");
+  const int with_norm = a->norm_w != nullptr;
+  CRF_CHECK(!with_norm || (dnorm_w && dnorm_b), "crf_layer_bwd: gradient buffers of the closing norm are missing");
+  const LayerLayout L = layer_layout(*d, a->depth, with_norm);
+  const LayerBwdLayout W = layer_bwd_layout(*d, a->depth, with_norm);
+  CRF_CHECK(ws_bytes >= W.total, "crf_layer_bwd: workspace too small (%zu < %zu)", ws_bytes, W.total);
+  DeviceGuard guard(d->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* S = static_cast<const uint8_t*>(saved);
+  uint8_t* Wk = static_cast<uint8_t*>(ws);
+  const size_t T = static_cast<size_t>(d->B) * d->H * d->W, C = d->C;
+
+  // gradient entering the last block: fp32 + bf16 twin
+  const float* g32 = static_cast<const float*>(dy);
+  const void* g16 = nullptr;
+  if (with_norm) {
+    const float* ylast = reinterpret_cast<const float*>(S + L.yout[a->depth - 1]);
+    float* gn = reinterpret_cast<float*>(Wk + W.g_f32);
+    // LayerNorm backward writes dx in fp32 and its bf16 twin in one pass (the MLP GEMMs read the twin)
+    if (a->out_dtype == CRF_DT_F32) {
+      if (launch_ln_bwd(static_cast<const float*>(dy), ylast, reinterpret_cast<const float*>(S + L.norm_stats), a->norm_w,
+                        nullptr, gn, Wk + W.g_bf16, dnorm_w, dnorm_b, static_cast<int>(T), d->C, st))
+        return 1;
+      g16 = Wk + W.g_bf16;
+    } else {
+      if (launch_layernorm_bwd(dy, CRF_DT_BF16, ylast, reinterpret_cast<const float*>(S + L.norm_stats), a->norm_w, gn,
+                               Wk + W.g_bf16, dnorm_w, dnorm_b, static_cast<int>(T), d->C, st))
+        return 1;
+      g16 = Wk + W.g_bf16;
+    }
+    g32 = gn;
+  }
+  for (int i = a->depth - 1; i >= 0; --i) {
+    const crf_block_desc bd = block_desc_of(*d, i);
+    const void* xin = i == 0 ? x : static_cast<const void*>(S + L.yout[i - 1]);
+    float* dxo = i == 0 ? dx : reinterpret_cast<float*>(Wk + W.mid_f32 + (i & 1) * align_up(T * C * 4));
+    void* dxo16 = i == 0 ? nullptr : static_cast<void*>(Wk + W.mid_bf16 + (i & 1) * align_up(T * C * 2));
+    if (block_bwd_impl(&bd, a->params + i, xin, S + L.vb, g32, g16, S + L.blk[i], dxo, dxo16, dv,
+                       i == a->depth - 1 ? 0 : 1, g + i, Wk + W.blk, bwd_layout(bd).total, stream))
+      return 1;
+    g32 = dxo;
+    g16 = dxo16;
+  }
   return 0;
 }
 
@@ -311,7 +479,8 @@ int crf_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* s
   CRF_CHECK(g && x && stats && gamma && dx && dgamma && dbeta && T > 0, "crf_layernorm_bwd: bad arguments");
   DeviceGuard guard(device);
   CRF_CHECK(guard.ok, "cannot select device %d", device);
-  return launch_layernorm_bwd(g, g_dtype, x, stats, gamma, dx, dgamma, dbeta, T, C, static_cast<cudaStream_t>(stream));
+  return launch_layernorm_bwd(g, g_dtype, x, stats, gamma, dx, nullptr, dgamma, dbeta, T, C,
+                              static_cast<cudaStream_t>(stream));
 }
 int crf_depth_loss_fwd(const void* pred, int pred_dtype, const float* target, int n_img, int H, int W, float* sums,
                        float* G, int device, void* stream) {

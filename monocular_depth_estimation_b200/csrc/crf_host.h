@@ -79,7 +79,7 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
                          float* stats, int T, int C, cudaStream_t st);
 int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
-                         float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
+                         void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
 int launch_depth_loss_fwd(const void* pred, int pred_dtype, const float* tgt, int n_img, int H, int W, float* sums,
                           float* G, cudaStream_t st);
 int launch_depth_loss_bwd(const void* pred, int pred_dtype, const float* tgt, const float* G, const float* gout,

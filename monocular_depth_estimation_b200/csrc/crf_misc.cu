@@ -475,7 +475,8 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 }
 
 int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
-                         float* dgamma, float* dbeta, int T, int C, cudaStream_t st) {
+                         void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st) {
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 64 in [64,1024]", C);
   CRF_CHECK(g_dtype == CRF_DT_F32 || g_dtype == CRF_DT_BF16, "layernorm_bwd: unsupported gradient dtype %d", g_dtype);
   int dev = 0;
@@ -488,10 +489,10 @@ int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float
   case NCH:                                                                                                            \
     if (g_dtype == CRF_DT_F32)                                                                                         \
       ln_bwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), x, stats, gamma, nullptr,   \
-                                                        dx, nullptr, dgamma, dbeta, T);                                \
+                                                        dx, dxb, dgamma, dbeta, T);                                    \
     else                                                                                                               \
       ln_bwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), x, stats,    \
-                                                                gamma, nullptr, dx, nullptr, dgamma, dbeta, T);        \
+                                                                gamma, nullptr, dx, dxb, dgamma, dbeta, T);            \
     break;
   switch (C / 64) {
     CRF_LNSB(1) CRF_LNSB(2) CRF_LNSB(3) CRF_LNSB(4) CRF_LNSB(5) CRF_LNSB(6) CRF_LNSB(7) CRF_LNSB(8) CRF_LNSB(9)

@@ -124,6 +124,106 @@ def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None
     return _CRFBlockFn.apply(x, v, v_bf16, H, W, num_heads, window, shift, float(qk_scale), float(eps), *params)
 
 
+class _CRFLayerFn(torch.autograd.Function):
+    """BasicCRFLayer.forward (/root/reference/src/newcrf_layers.py:323-363) -- `depth` blocks, shift alternating 0 and
+    window // 2, the same v for all -- optionally closed by NewCRF.norm_crf (:430-431): one C call each way
+    (crf_layer_fwd / crf_layer_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, v, H, W, num_heads, window, qk_scale, eps, out_bf16, depth, norm_w, norm_b, *params):
+        B, Ltok, Cd = x.shape
+        dev = x.device
+        params = tuple(p.detach().contiguous() for p in params)
+        assert len(params) == 13 * depth
+        with_norm = norm_w is not None
+        training = any(ctx.needs_input_grad)
+        xd, v_arg = x.detach(), v.detach()
+        if v_arg.stride(1) != W * v_arg.stride(2):
+            v_arg = v_arg.contiguous()
+        desc = make_desc(B, H, W, Cd, num_heads, 0, window=window, training=training, device=dev.index, x=xd, v=v_arg)
+        sb, wb = C.c_size_t(), C.c_size_t()
+        L.check(L.lib().crf_layer_sizes(C.byref(desc), depth, int(with_norm), C.byref(sb), C.byref(wb)),
+                "crf_layer_sizes")
+        saved = torch.empty(sb.value, dtype=torch.uint8, device=dev)
+        y = torch.empty(B, Ltok, Cd, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        pa = (L.BlockParams * depth)()
+        for i in range(depth):
+            for name, t in zip(L.PARAM_NAMES, params[13 * i:13 * i + 13]):
+                setattr(pa[i], name, t.data_ptr())
+            pa[i].qk_scale, pa[i].ln_eps = float(qk_scale), float(eps)
+        nw = norm_w.detach().contiguous() if with_norm else None
+        nb = norm_b.detach().contiguous() if with_norm else None
+        la = L.LayerArgs(depth, L.CRF_DT_BF16 if out_bf16 else L.CRF_DT_F32, pa,
+                         nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None)
+        L.check(L.lib().crf_layer_fwd(C.byref(desc), C.byref(la), xd.data_ptr(), v_arg.data_ptr(), y.data_ptr(),
+                                      saved.data_ptr(), _stream_ptr(dev)), "crf_layer_fwd")
+        if training:
+            ctx.save_for_backward(xd, v_arg, saved, *((nw, nb) if with_norm else ()), *params)
+            ctx.desc = desc
+            ctx.meta = (H, W, qk_scale, eps, out_bf16, depth, with_norm, wb.value)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        H, W, qk_scale, eps, out_bf16, depth, with_norm, ws_bytes = ctx.meta
+        xd, v_arg, saved, *rest = ctx.saved_tensors
+        nw, nb = (rest[0], rest[1]) if with_norm else (None, None)
+        params = rest[2:] if with_norm else rest
+        desc, dev = ctx.desc, xd.device
+        B, Ltok, Cd = xd.shape
+        dy = dy.contiguous().to(torch.bfloat16 if out_bf16 else torch.float32)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        dx = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
+        dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
+        # one zero-filled buffer for every parameter gradient (256-byte aligned views)
+        shapes = [p.shape for p in params] + ([nw.shape, nb.shape] if with_norm else [])
+        offs, o = [], 0
+        for shp in shapes:
+            offs.append(o)
+            o += (shp.numel() + 63) // 64 * 64
+        flat = torch.zeros(o, dtype=torch.float32, device=dev)
+        views = [flat[a:a + shp.numel()].view(shp) for a, shp in zip(offs, shapes)]
+        pa, ga = (L.BlockParams * depth)(), (L.BlockGrads * depth)()
+        for i in range(depth):
+            for k, name in enumerate(L.PARAM_NAMES):
+                setattr(pa[i], name, params[13 * i + k].data_ptr())
+                setattr(ga[i], name, views[13 * i + k].data_ptr())
+            pa[i].qk_scale, pa[i].ln_eps = float(qk_scale), float(eps)
+        la = L.LayerArgs(depth, L.CRF_DT_BF16 if out_bf16 else L.CRF_DT_F32, pa,
+                         nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None)
+        dnw = views[13 * depth].data_ptr() if with_norm else None
+        dnb = views[13 * depth + 1].data_ptr() if with_norm else None
+        L.check(L.lib().crf_layer_bwd(C.byref(desc), C.byref(la), xd.data_ptr(), v_arg.data_ptr(), dy.data_ptr(),
+                                      saved.data_ptr(), dx.data_ptr(), dv.data_ptr(), ga, dnw, dnb, ws.data_ptr(),
+                                      ws.numel(), _stream_ptr(dev)), "crf_layer_bwd")
+        gn = (views[13 * depth], views[13 * depth + 1]) if with_norm else (None, None)
+        return (dx, dv, None, None, None, None, None, None, None, None, gn[0], gn[1], *views[:13 * depth])
+
+
+def crf_layer(x, v, H, W, block_params, num_heads, *, window=7, qk_scale=None, eps=1e-5, norm=None, out_dtype=None):
+    """BasicCRFLayer.forward as one call: block_params = [13 tensors in PARAM_KEYS order] per block (shift 0,
+    window // 2, 0, ...); norm = (weight, bias) of a closing LayerNorm or None; out_dtype torch.bfloat16 only with
+    norm.  Returns (B, H*W, C).  Mirrors the reference's error behaviour (newcrf_layers.py:205,143)."""
+    assert x.dim() == 3 and v.dim() == 4
+    B, Ltok, Cd = x.shape
+    assert Ltok == H * W, "input feature has wrong size"
+    assert Cd == v.shape[-1], "self.dim != v.shape[-1]"
+    if not x.is_cuda:
+        raise RuntimeError("monocular_depth_estimation_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if v.dtype not in (torch.float32, torch.bfloat16):
+        v = v.float()
+    if qk_scale is None:
+        qk_scale = (Cd // num_heads) ** -0.5
+    flat = [t for blk in block_params for t in blk]
+    nw, nb = norm if norm is not None else (None, None)
+    out_bf16 = out_dtype == torch.bfloat16
+    assert not out_bf16 or norm is not None, "bf16 output needs the closing LayerNorm"
+    return _CRFLayerFn.apply(x, v, H, W, num_heads, window, float(qk_scale), float(eps), out_bf16, len(block_params),
+                             nw, nb, *flat)
+
+
 class _LayerNormFn(torch.autograd.Function):
     """LayerNorm over the last dim of contiguous fp32 token rows (the stage-closing `norm_crf`,
     /root/reference/src/newcrf_layers.py:430-431) on the library's row kernels; output fp32, or bf16 when asked."""

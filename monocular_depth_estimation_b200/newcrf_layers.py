@@ -150,12 +150,35 @@ class BasicCRFLayer(nn.Module):
             for i in range(depth)])
         self.downsample = None
 
-    def forward(self, x, v, H, W):
-        """x: (B, H*W, C); v: (B, H, W, C), the same for every block.  Returns (x, H, W, x, H, W)."""
-        v_bf16 = CF.convert_v(v) if (v.is_cuda and self.depth > 1) else None  # both blocks read the same v
+    def _fusable(self, x):
+        """One crf_layer_fwd / crf_layer_bwd call covers the whole layer when the blocks are the stock alternation."""
+        blk0 = self.blocks[0]
+        return (x.is_cuda and 1 <= self.depth <= 8
+                and all(b.shift_size == (0 if i % 2 == 0 else self.window_size // 2) and b.num_heads == blk0.num_heads
+                        and b.window_size == self.window_size and b.norm1.eps == blk0.norm1.eps
+                        and b.attn.scale == blk0.attn.scale for i, b in enumerate(self.blocks)))
+
+    def run(self, x, v, H, W, norm=None, out_dtype=None):
+        """The layer, optionally closed by `norm` (an nn.LayerNorm: NewCRF.norm_crf) -> (B, H*W, C)."""
         for blk in self.blocks:
             blk.H, blk.W = H, W
+        if self._fusable(x) and (norm is None or (type(norm) is nn.LayerNorm and norm.elementwise_affine
+                                                  and norm.eps == self.blocks[0].norm1.eps)):
+            blk0 = self.blocks[0]
+            assert x.shape[1] == H * W, "input feature has wrong size"
+            return CF.crf_layer(x, v, H, W, [b.fused_params() for b in self.blocks], blk0.num_heads,
+                                window=self.window_size, qk_scale=blk0.attn.scale, eps=blk0.norm1.eps,
+                                norm=None if norm is None else (norm.weight, norm.bias), out_dtype=out_dtype)
+        v_bf16 = CF.convert_v(v) if (v.is_cuda and self.depth > 1) else None  # both blocks read the same v
+        for blk in self.blocks:
             x = blk(x, v, None, v_bf16=v_bf16)
+        if norm is not None:
+            x = norm(x)
+        return x
+
+    def forward(self, x, v, H, W):
+        """x: (B, H*W, C); v: (B, H, W, C), the same for every block.  Returns (x, H, W, x, H, W)."""
+        x = self.run(x, v, H, W)
         return x, H, W, x, H, W
 
 
@@ -215,16 +238,11 @@ class NewCRF(nn.Module):
         B, Cd, Wh, Ww = x.shape
         tokens = x.flatten(2).transpose(1, 2)      # (B, H*W, C) view of NCHW -- the kernel reads it strided
         v_hwc = v.permute(0, 2, 3, 1)              # (B, H, W, C) view of NCHW
-        y = self.crf_layer(tokens, v_hwc, Wh, Ww)[0]
-        if (y.is_cuda and type(self.norm_crf) is nn.LayerNorm and self.norm_crf.elementwise_affine
-                and self.embed_dim % 64 == 0 and self.embed_dim <= 1024):
-            # library row kernel; under bf16 autocast it emits bf16 directly (the next consumer is a convolution that
-            # would cast the fp32 result anyway -- same values, one pass less)
-            bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
-            y = CF.layer_norm(y, self.norm_crf.weight, self.norm_crf.bias, self.norm_crf.eps,
-                              out_dtype=torch.bfloat16 if bf16 else torch.float32)
-        else:
-            y = self.norm_crf(y)
+        # the layer and the closing norm in one library call; under bf16 autocast the result is emitted in bf16 (the
+        # next consumer is a convolution that would cast the fp32 result anyway -- same values, one pass less)
+        bf16 = x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        y = self.crf_layer.run(tokens, v_hwc, Wh, Ww, norm=self.norm_crf,
+                               out_dtype=torch.bfloat16 if bf16 else torch.float32)
         out = y.view(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2)
         if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
             return out  # channels-last pipeline: the token-major result already IS NHWC memory, no copy needed

@@ -58,6 +58,56 @@ def test_layer_matches_reference_golden(name):
     assert not bad, f"rel_l2 above {TOL}: {bad}\nall: {errs}"
 
 
+@pytest.mark.parametrize("with_norm,out_bf16", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("B,H,W,C,nH,depth", [(2, 9, 10, 64, 2, 2), (2, 15, 20, 128, 4, 3), (1, 30, 40, 256, 8, 1)])
+def test_layer_call_equals_block_by_block(B, H, W, C, nH, depth, with_norm, out_bf16):
+    """crf_layer_fwd / crf_layer_bwd (one call per BasicCRFLayer incl. the closing norm_crf) against the same layer run
+    block by block through crf_block_fwd / crf_block_bwd + the stand-alone LayerNorm: same kernels, same order of
+    fp32 operations -> outputs, dx, dv and every parameter gradient must agree to fp32 round-off (the bf16 twins the
+    layer call hands between blocks are bit-identical to the casts the block path makes)."""
+    pkg = _pkg()
+    from monocular_depth_estimation_b200 import functional as CF
+    torch.manual_seed(7 * depth + C)
+    layer = pkg.BasicCRFLayer(dim=C, depth=depth, num_heads=nH, v_dim=C).to(DEV)
+    norm = torch.nn.LayerNorm(C).to(DEV) if with_norm else None
+    if norm is not None:
+        with torch.no_grad():
+            norm.weight.normal_(1.0, 0.2)
+            norm.bias.normal_(0.0, 0.2)
+    x0 = torch.randn(B, C, H, W, device=DEV).flatten(2).transpose(1, 2)
+    v0 = torch.randn(B, C, H, W, device=DEV).permute(0, 2, 3, 1)
+    gy = torch.randn(B, H * W, C, device=DEV)
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+
+    def run(fused):
+        for p_ in list(layer.parameters()) + (list(norm.parameters()) if norm is not None else []):
+            p_.grad = None
+        x = x0.detach().clone().requires_grad_(True) if False else x0.detach().requires_grad_(True)
+        v = v0.detach().requires_grad_(True)
+        if fused:
+            y = layer.run(x, v, H, W, norm=norm, out_dtype=odt)
+        else:
+            vb = CF.convert_v(v)
+            y = x
+            for blk in layer.blocks:
+                blk.H, blk.W = H, W
+                y = blk(y, v, None, v_bf16=vb)
+            if norm is not None:
+                y = CF.layer_norm(y, norm.weight, norm.bias, norm.eps, out_dtype=odt)
+        y.backward(gy.to(y.dtype))
+        grads = {k: p_.grad.clone() for k, p_ in layer.named_parameters()}
+        if norm is not None:
+            grads.update({"norm." + k: p_.grad.clone() for k, p_ in norm.named_parameters()})
+        return y.detach().float(), x.grad.clone(), v.grad.clone(), grads
+
+    yf, dxf, dvf, gf = run(True)
+    yb, dxb, dvb, gb = run(False)
+    assert yf.dtype == yb.dtype and torch.equal(yf, yb), "forward differs"
+    assert rel_l2(dxf, dxb) < 1e-6 and rel_l2(dvf, dvb) < 1e-6, (rel_l2(dxf, dxb), rel_l2(dvf, dvb))
+    bad = {k: rel_l2(gf[k], gb[k]) for k in gb if not rel_l2(gf[k], gb[k]) < 1e-5}
+    assert not bad, bad
+
+
 def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device):
     from monocular_depth_estimation_b200 import functional as CF
     gen = torch.Generator().manual_seed(seed)
