@@ -123,7 +123,8 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
  *   d      : descriptor of the layer's input x / v (the shift field is ignored; blocks after the first read the
  *            previous block's contiguous fp32 output)
  *   y      : (B, H*W, C) contiguous, f32, or bf16 when out_dtype == CRF_DT_BF16 (needs the closing norm)
- *   dy     : gradient of y in y's dtype; dx (B, H*W, C) f32; dv (B, H, W, C) f32 (overwritten)
+ *   dy     : gradient of y in y's dtype; dx (B, H*W, C) contiguous in x's dtype (f32 or bf16); dv (B, H, W, C) f32
+ *            (both overwritten)
  *   g      : `depth` gradient structs (accumulated, +=); dnorm_w / dnorm_b accumulated, NULL without the norm
  * ------------------------------------------------------------------------------------------------------ */
 #define CRF_MAX_DEPTH 8
@@ -138,7 +139,7 @@ int crf_layer_sizes(const crf_block_desc* d, int depth, int with_norm, size_t* s
 int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, void* y, void* saved,
                   void* stream);
 int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, const void* dy,
-                  const void* saved, float* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
+                  const void* saved, void* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
                   void* ws, size_t ws_bytes, void* stream);
 
 /* v (B,H,W,C), any strides, fp32/bf16 -> bf16 token-major (T, C) contiguous; done once per BasicCRFLayer

@@ -215,7 +215,7 @@ static int block_bwd_impl(const crf_block_desc* d, const crf_block_params* p, co
                           const float* dy, const void* dy_bf16, const void* saved, float* dx, void* dx_bf16, float* dv,
                           int dv_accumulate, const crf_block_grads* g, void* ws, size_t ws_bytes, void* stream) {
   if (check_desc(d)) return 1;
-  CRF_CHECK(p && x && v && dy && saved && dx && dv && g && ws, "crf_block_bwd: null pointer");
+  CRF_CHECK(p && x && v && dy && saved && (dx || dx_bf16) && dv && g && ws, "crf_block_bwd: null pointer");
   CRF_CHECK(d->training, "crf_block_bwd: forward was not run with training=1");
   const BwdLayout W = bwd_layout(*d);
   CRF_CHECK(ws_bytes >= W.total, "crf_block_bwd: workspace too small (%zu < %zu)", ws_bytes, W.total);
@@ -372,7 +372,7 @@ int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
 }
 
 int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, const void* dy,
-                  const void* saved, float* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
+                  const void* saved, void* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
                   void* ws, size_t ws_bytes, void* stream) {
   (void)v;
   if (check_layer(d, a)) return 1;
@@ -413,8 +413,12 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
   for (int i = a->depth - 1; i >= 0; --i) {
     const crf_block_desc bd = block_desc_of(*d, i);
     const void* xin = i == 0 ? x : static_cast<const void*>(S + L.yout[i - 1]);
-    float* dxo = i == 0 ? dx : reinterpret_cast<float*>(Wk + W.mid_f32 + (i & 1) * align_up(T * C * 4));
-    void* dxo16 = i == 0 ? nullptr : static_cast<void*>(Wk + W.mid_bf16 + (i & 1) * align_up(T * C * 2));
+    // the layer's dx leaves in the dtype of x: bf16 inputs get a bf16 gradient straight from the LayerNorm backward
+    const bool dx_is_bf16 = d->x_dtype == CRF_DT_BF16;
+    float* dxo = i == 0 ? (dx_is_bf16 ? nullptr : static_cast<float*>(dx))
+                        : reinterpret_cast<float*>(Wk + W.mid_f32 + (i & 1) * align_up(T * C * 4));
+    void* dxo16 = i == 0 ? (dx_is_bf16 ? dx : nullptr)
+                         : static_cast<void*>(Wk + W.mid_bf16 + (i & 1) * align_up(T * C * 2));
     if (block_bwd_impl(&bd, a->params + i, xin, S + L.vb, g32, g16, S + L.blk[i], dxo, dxo16, dv,
                        i == a->depth - 1 ? 0 : 1, g + i, Wk + W.blk, bwd_layout(bd).total, stream))
       return 1;

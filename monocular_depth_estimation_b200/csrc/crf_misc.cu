@@ -195,7 +195,7 @@ ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float
         const float2 r = __ldg(reinterpret_cast<const float2*>(dres + off));
         o0 += r.x; o1 += r.y;
       }
-      *reinterpret_cast<float2*>(dx + off) = make_float2(o0, o1);
+      if (dx != nullptr) *reinterpret_cast<float2*>(dx + off) = make_float2(o0, o1);
       if (dx_bf16 != nullptr) *reinterpret_cast<uint32_t*>(dx_bf16 + off) = pack_bf16(o0, o1);
     }
   }

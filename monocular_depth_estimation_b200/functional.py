@@ -173,7 +173,7 @@ class _CRFLayerFn(torch.autograd.Function):
         B, Ltok, Cd = xd.shape
         dy = dy.contiguous().to(torch.bfloat16 if out_bf16 else torch.float32)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        dx = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
+        dx = torch.empty(B, Ltok, Cd, dtype=xd.dtype, device=dev)   # in x's dtype: no autograd cast afterwards
         dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
         # one zero-filled buffer for every parameter gradient (256-byte aligned views)
         shapes = [p.shape for p in params] + ([nw.shape, nb.shape] if with_norm else [])

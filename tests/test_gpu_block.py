@@ -108,6 +108,38 @@ def test_layer_call_equals_block_by_block(B, H, W, C, nH, depth, with_norm, out_
     assert not bad, bad
 
 
+def test_layer_call_bf16_inputs_gradient_dtype():
+    """bf16 x / v (the autocast pipeline): the layer call returns dx in bf16 straight from the LayerNorm backward; it must
+    equal the block-by-block path, whose fp32 dx autograd rounds to bf16 afterwards."""
+    pkg = _pkg()
+    from monocular_depth_estimation_b200 import functional as CF
+    torch.manual_seed(11)
+    B, H, W, C, nH = 2, 15, 20, 128, 4
+    layer = pkg.BasicCRFLayer(dim=C, depth=2, num_heads=nH, v_dim=C).to(DEV)
+    xs = torch.randn(B, H, W, C, device=DEV).to(torch.bfloat16)      # channels-last conv output: token-major rows
+    vs = torch.randn(B, H, W, C, device=DEV).to(torch.bfloat16)
+    gy = torch.randn(B, H * W, C, device=DEV)
+    outs = []
+    for fused in (True, False):
+        x = xs.view(B, H * W, C).detach().requires_grad_(True)
+        v = vs.detach().requires_grad_(True)
+        if fused:
+            y = layer.run(x, v, H, W)
+        else:
+            vb = CF.convert_v(v)
+            y = x
+            for blk in layer.blocks:
+                blk.H, blk.W = H, W
+                y = blk(y, v, None, v_bf16=vb)
+        y.backward(gy)
+        assert x.grad.dtype == torch.bfloat16 and v.grad.dtype == torch.bfloat16
+        outs.append((y.detach(), x.grad.clone(), v.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1]), rel_l2(outs[0][1].float(), outs[1][1].float())
+    # dv: the block path sums two bf16-rounded gradients in bf16 (autograd), the layer call rounds the fp32 sum once
+    assert rel_l2(outs[0][2].float(), outs[1][2].float()) < 1e-2
+
+
 def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device):
     from monocular_depth_estimation_b200 import functional as CF
     gen = torch.Generator().manual_seed(seed)
