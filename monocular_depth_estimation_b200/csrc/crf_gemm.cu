@@ -171,7 +171,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t out0_s = smem_base, x_s = smem_base + 2 * kSlabBytes;
     uint8_t* out0_g = smem_gen;
     uint8_t* x_g = smem_gen + 2 * kSlabBytes;
-    const int out_row0 = (EPI == CRF_EPI_SPLITK_F32) ? static_cast<int>(blockIdx.z) * ep.m_pad + m0 : m0;
+    const bool tma_red = (EPI == CRF_EPI_SPLITK_F32) && ep.tma_reduce != 0;
+    const int out_row0 = (EPI == CRF_EPI_SPLITK_F32 && !tma_red) ? static_cast<int>(blockIdx.z) * ep.m_pad + m0 : m0;
 
     if (kHasAux && r == 0 && e < kNumSlabs) {
       mbar_expect_tx(aux_bar(e), kSlabBytes);
@@ -195,7 +196,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       fence_proxy_async_smem();
       named_bar_sync(3 + e, 128);
       if (r == 0) {
-        if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s + buf * kSlabBytes, nc, out_row0);
+        if (tma_red) tma_reduce_add_2d(&tmO0, out0_s + buf * kSlabBytes, nc, out_row0);
+        else if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s + buf * kSlabBytes, nc, out_row0);
         if (kHasOut1) tma_store_2d(&tmO1, x_s + buf * kSlabBytes, nc, out_row0);
         bulk_commit();
         if (kHasAux && s + 2 < kNumSlabs) {  // the aux slab was consumed before the barrier above: refill it
@@ -243,6 +245,7 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, in
 struct Launch {
   CUtensorMap tmA, tmB, tmO0, tmO1, tmAux;
   int total_chunks, cps, splits, m_pad;
+  int tma_reduce = 0;
 };
 
 template <int BN, int EPI>
@@ -260,7 +263,8 @@ int launch_one(const Launch& L, const crf_gemm_args& a, cudaStream_t st) {
   const size_t smem = ring + 1024 + 8 * (2 * stages + 4) + 1024;  // + align slack, barriers, ones tile
   auto kern = gemm_kernel<BN, EPI>;
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  EpiParams ep{a.bias, a.scale, a.scale_cols, L.m_pad, a.out0 != nullptr ? 1 : 0, a.a_major == 1 ? a.colsum : nullptr};
+  EpiParams ep{a.bias, a.scale, a.scale_cols, L.m_pad, a.out0 != nullptr ? 1 : 0, a.a_major == 1 ? a.colsum : nullptr,
+               L.tma_reduce};
   dim3 grid((a.M + BM - 1) / BM, a.N / BN, L.splits);
   const double mn = static_cast<double>(a.M) * a.N;
   const double out_bytes = EPI == CRF_EPI_STORE_BF16 ? 2 * mn
@@ -361,7 +365,8 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
     gemm_splitk_workspace_bytes(a.M, a.N, a.K, a.device, &splits);
     if (a.split_k > 0 && a.split_k < splits) splits = a.split_k;
     const size_t per_split = static_cast<size_t>(L.m_pad) * a.N * sizeof(float);
-    if (splits > 1) {
+    static const bool deterministic = getenv("CRF_WGRAD_DETERMINISTIC") != nullptr && atoi(getenv("CRF_WGRAD_DETERMINISTIC")) != 0;
+    if (splits > 1 && deterministic) {  // the partial tiles must fit the caller's workspace
       const size_t fit = a.workspace == nullptr ? 0 : a.workspace_bytes / per_split;
       if (fit < static_cast<size_t>(splits)) splits = fit < 1 ? 1 : static_cast<int>(fit);
     }
@@ -374,6 +379,14 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
     }
     L.cps = (L.total_chunks + splits - 1) / splits;
     L.splits = (L.total_chunks + L.cps - 1) / L.cps;  // no empty split
+    // Default: every split ADDS its fp32 tile into dW with a TMA reduction (cp.reduce.async.bulk.tensor .add): no
+    // partial buffer, no reduce kernel; the sum over splits is formed by the L2 in arrival order (fp32 round-off
+    // depends on it).  CRF_WGRAD_DETERMINISTIC=1 keeps the partial tiles + fixed-order reduce kernel.
+    if (!deterministic) {
+      L.tma_reduce = 1;
+      if (make_tmap_f32(&L.tmO0, a.out0, a.M, a.N, BM)) return 1;
+      return launch_bn_dispatch(BN, L, b, epi, st);
+    }
     if (make_tmap_f32(&L.tmO0, a.workspace, static_cast<uint64_t>(L.splits) * L.m_pad, a.N, BM)) return 1;
     if (launch_bn_dispatch(BN, L, b, epi, st)) return 1;
     const int64_t total4 = static_cast<int64_t>(a.M) * a.N / 4;

@@ -13,6 +13,7 @@ struct EpiParams {
   int m_pad;       // split-K: rows per split in the partial buffer
   int store_out0;  // BIAS_GELU: 0 -> skip the pre-activation output (inference)
   float* colsum;   // wgrad only: colsum[m] += sum_k A(m,k)  (the bias gradient), or nullptr
+  int tma_reduce;  // split-K: 1 -> every split adds its tile into the output with a TMA reduction (no partial buffer)
 };
 
 __device__ __forceinline__ void add_bias32(float (&v)[32], const float* bias, int n) {
