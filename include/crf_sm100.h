@@ -233,7 +233,7 @@ int crf_depth_loss_bwd(const void* pred, int pred_dtype, const float* target, co
  * B, H, W, C always describe the (B, H, W, C) side; C % 4 == 0. */
 int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, int inverse, int device,
                            void* stream);
-/* out[n] += sum_t g[t, n], g bf16 (T, N) */
+/* out[n] += sum_t g[t, n], g bf16 (T, N) contiguous, N % 4 == 0 */
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
 /* f32 -> bf16 contiguous */
 int crf_cast_bf16(const float* src, void* dst, int64_t n, int device, void* stream);

@@ -223,20 +223,32 @@ ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out, int T, int N, int rows_per_cta) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
-  if (c >= N) return;
+  // threadIdx.x: column quad (4 columns, one 8-byte load); threadIdx.y: row lane, so that narrow matrices (N = 128:
+  // 32 column threads) still keep 256 loads in flight per CTA; row lanes are combined through shared memory.
+  __shared__ float red[256][4];
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(T, r0 + rows_per_cta);
-  float s0 = 0.f, s1 = 0.f;
-  const __nv_bfloat16* p = g + static_cast<int64_t>(r0) * N + c;
-#pragma unroll 4
-  for (int r = r0; r < r1; ++r, p += N) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
-    s0 += bf16_lo(w);
-    s1 += bf16_hi(w);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < N) {
+    const __nv_bfloat16* p = g + static_cast<int64_t>(r0 + threadIdx.y) * N + c;
+    const int64_t step = static_cast<int64_t>(blockDim.y) * N;
+#pragma unroll 8
+    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y, p += step) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+      s0 += bf16_lo(w.x); s1 += bf16_hi(w.x); s2 += bf16_lo(w.y); s3 += bf16_hi(w.y);
+    }
   }
-  atomicAdd(out + c, s0);
-  atomicAdd(out + c + 1, s1);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  red[tid][0] = s0; red[tid][1] = s1; red[tid][2] = s2; red[tid][3] = s3;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    for (int y = 1; y < blockDim.y; ++y) {
+      const float* q = red[y * blockDim.x + threadIdx.x];
+      s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
+    }
+    atomicAdd(out + c, s0); atomicAdd(out + c + 1, s1); atomicAdd(out + c + 2, s2); atomicAdd(out + c + 3, s3);
+  }
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -531,16 +543,24 @@ int launch_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int 
 }
 
 int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st) {
-  CRF_CHECK(N % 2 == 0, "colsum: N must be even");
+  CRF_CHECK(N % 4 == 0, "colsum: N must be a multiple of 4");
   int dev = 0;
   cudaGetDevice(&dev);
-  const int gx = (N / 2 + 255) / 256;
-  int gy = (num_sms(dev) * 4 + gx - 1) / gx;
+  int bx = N / 4;                       // column quads
+  if (bx > 256) bx = 256;
+  int bxp = 1;
+  while (bxp < bx) bxp <<= 1;           // power of two so that bx * by == 256
+  bx = bxp;
+  const int by = 256 / bx;
+  const int gx = (N / 4 + bx - 1) / bx;
+  // two CTAs per SM: enough loads in flight for the HBM, few enough CTAs that the same-address atomics at the end
+  // (one per column and CTA) stay cheap
+  int gy = (num_sms(dev) * 2 + gx - 1) / gx;
   int rows = (T + gy - 1) / gy;
   if (rows < 32) rows = 32;
   gy = (T + rows - 1) / rows;
   KernelTimer tm(st, 0.0, 2.0 * T * N, "colsum_T%d_N%d", T, N);
-  colsum_bf16_kernel<<<dim3(gx, gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
+  colsum_bf16_kernel<<<dim3(gx, gy), dim3(bx, by), 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;
