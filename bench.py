@@ -58,6 +58,8 @@ def parse_args():
                          "2: also at N>1 (DDP all-reduce captured in the graph); 0: eager")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
+    ap.add_argument("--cudnn-benchmark", type=int, default=0,
+                    help="1: torch.backends.cudnn.benchmark (cuDNN autotunes the stock convolutions during warm-up)")
     ap.add_argument("--memory-format", default="channels_last", choices=["contiguous", "channels_last"],
                     help="memory format of the model and the images (host-side choice; math is identical)")
     return ap.parse_args()
@@ -184,6 +186,7 @@ def run_ours(args):
     rank, local_rank, world, device = init_distributed()
     torch.cuda.set_device(device)
     torch.manual_seed(1234 + rank)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     B, H, W = args.batch, args.height, args.width
 
     model = PTModel().to(device).train()
