@@ -71,7 +71,8 @@ def wrap_ddp(model, device, world):
     if device.type == "cuda":
         # broadcast_buffers=False: BatchNorm running statistics stay rank-local (46 BN layers would otherwise add a
         # broadcast of ~140 small buffers to every forward); gradients are what is averaged.
-        return DDP(model, device_ids=[device.index], bucket_cap_mb=64, broadcast_buffers=False)
+        return DDP(model, device_ids=[device.index], bucket_cap_mb=64, broadcast_buffers=False,
+                   gradient_as_bucket_view=os.environ.get("CRF_DDP_BUCKET_VIEW", "1") != "0")
     return DDP(model)
 
 
