@@ -1,6 +1,24 @@
-// Window-attention kernels, third generation (default): same math and tile formats as crf_attn_pipe.cu (see the
-// header comments there and in crf_attn.cu), restructured after per-phase cycle counts (CRF_ATTN_PROF=1) showed where
-// a window pair's time goes.  Nothing on the per-pair chain
+// Window-attention core of the CRF block on tcgen05, forward and backward.
+//
+// Replaces, without materialising any of them in HBM: F.pad, torch.roll, window_partition of x and v, the
+// relative-position-bias gather, the shifted-window mask, softmax, attn @ v, window_reverse, the reverse roll and
+// the crop (newcrf_layers.py:121-146, :212-249, :332-350).
+//
+// Work decomposition: a CTA owns one head and loops over PAIRS of windows.  The two 49-token windows of a pair are
+// stacked into one 128-row UMMA tile (rows 0..48 = window A, 64..112 = window B, the rest zero):
+//   S  [128 x 128] = bias + Q[128 x hd] * [K_A ; K_B]^T     -- row r only uses the 64 columns of its own window
+//   O  [128 x 2hd] = P~[128 x 64] * [V_A | V_B]             -- row r reads the hd columns of its window
+// Token rows are gathered straight from the token-major q/k/v tensors with the closed-form pad+roll index map
+// (cp.async 16-byte copies into the swizzled UMMA layout); zero-padded tokens get k = bias, v = 0 exactly as the
+// reference's pad-after-LayerNorm produces.  Softmax runs one thread per accumulator row (TMEM lane), fp32.
+// Backward recomputes S and P from q, k and the saved row log-sum-exp:
+//   dP = dO * [V_A;V_B]^T,  dS = P o (dP - rowsum(P o dP)),  per window w: dV_w = P_w^T dO_w, dK_w = dS_w^T Q_w,
+//   dQ_w = dS_w K_w;  the relative-position-bias gradient is accumulated in registers across all pairs a CTA
+//   processes (each thread owns one query row) and flushed once per CTA.
+//
+// This is the third generation of these kernels (single-buffer -> warp-specialised double-buffered -> this one),
+// restructured after per-phase cycle counts (CRF_ATTN_PROF=1) showed where a window pair's time goes.  Nothing on the
+// per-pair chain
 //   gather -> S (/dP) MMA -> softmax (/dS) math -> second-stage MMAs -> stores
 // waits for something it does not depend on, and the issue-bound softmax warps do less per element:
 //

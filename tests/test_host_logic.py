@@ -53,3 +53,35 @@ def test_model_tree_matches_reference_prefixes():
     assert "Unet.0.original_model.features.0.0.weight" in keys
     n = sum(p.numel() for p in m.parameters())
     assert abs(n / 1e6 - 45.07) < 3.0   # 45.07 M (encoder incl. the unused classifier here)
+
+
+def test_glue_host_paths_without_cuda():
+    """The glue around the hot path keeps stock-PyTorch behaviour for CPU tensors (the gloo tests run the model's
+    host logic on CPU), while everything that IS the hot path refuses to run without CUDA."""
+    import torch.nn.functional as F
+    from monocular_depth_estimation_b200 import functional as CF
+    from monocular_depth_estimation_b200 import newcrf_layers as NL
+    from monocular_depth_estimation_b200 import training as TR
+    from oracle import model_oracle as MO
+    torch.manual_seed(0)
+    # PixelShuffle(2): falls through to torch on CPU
+    x = torch.randn(2, 8, 3, 5)
+    assert torch.equal(CF.pixel_shuffle2(x), F.pixel_shuffle(x, 2))
+    # projection conv + bias: plain conv on CPU; the backward of the bias Function sums over (B, H, W)
+    conv = torch.nn.Conv2d(4, 6, 3, padding=1)
+    inp = torch.randn(2, 4, 5, 7)
+    assert torch.equal(NL._project(conv, inp), conv(inp))
+    y = torch.randn(2, 6, 5, 7, requires_grad=True)
+    b = torch.randn(6, requires_grad=True)
+    g = torch.randn(2, 6, 5, 7)
+    NL._ConvBiasFn.apply(y, b).backward(g)
+    assert torch.allclose(b.grad, g.sum((0, 2, 3)), atol=1e-5) and torch.equal(y.grad, g)
+    # loss: CPU composition of torch ops == the oracle's
+    p, t = torch.rand(2, 1, 9, 11), torch.rand(2, 1, 9, 11)
+    assert torch.allclose(TR.depth_loss(p, t), MO.ssim_l1_loss(p, t), atol=1e-6)
+    # the hot path itself has no CPU path
+    for call in (lambda: CF.layer_norm(torch.randn(4, 64), torch.ones(64), torch.zeros(64)),
+                 lambda: CF.depth_loss(p, t),
+                 lambda: CF.crf_layer(torch.randn(1, 49, 64), torch.randn(1, 7, 7, 64), 7, 7, [[None] * 13], 2)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
