@@ -309,7 +309,7 @@ LayerLayout layer_layout(const crf_block_desc& d, int depth, int with_norm) {
   return L;
 }
 struct LayerBwdLayout {
-  size_t blk, g_f32, g_bf16, mid_f32, mid_bf16, total;
+  size_t blk, g_f32, g_bf16, mid_f32[2], mid_bf16[2], total;
 };
 LayerBwdLayout layer_bwd_layout(const crf_block_desc& d, int depth, int with_norm) {
   LayerBwdLayout L{};
@@ -319,8 +319,10 @@ LayerBwdLayout layer_bwd_layout(const crf_block_desc& d, int depth, int with_nor
   L.blk = take(bwd_layout(block_desc_of(d, depth > 1 ? 1 : 0)).total);
   L.g_f32 = take(with_norm ? T * C * 4 : 0);
   L.g_bf16 = take(with_norm ? T * C * 2 : 0);
-  L.mid_f32 = take(depth > 1 ? 2 * T * C * 4 : 0);   // ping-pong buffers for the gradient between blocks
-  L.mid_bf16 = take(depth > 1 ? 2 * T * C * 2 : 0);
+  for (int k = 0; k < 2; ++k) {  // ping-pong buffers for the gradient between blocks (each slot aligned on its own)
+    L.mid_f32[k] = take(depth > 1 ? T * C * 4 : 0);
+    L.mid_bf16[k] = take(depth > 1 ? T * C * 2 : 0);
+  }
   L.total = o;
   return L;
 }
@@ -388,7 +390,7 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t* S = static_cast<const uint8_t*>(saved);
   uint8_t* Wk = static_cast<uint8_t*>(ws);
-  const size_t T = static_cast<size_t>(d->B) * d->H * d->W, C = d->C;
+  const size_t T = static_cast<size_t>(d->B) * d->H * d->W;
 
   // gradient entering the last block: fp32 + bf16 twin
   const float* g32 = static_cast<const float*>(dy);
@@ -416,9 +418,9 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
     // the layer's dx leaves in the dtype of x: bf16 inputs get a bf16 gradient straight from the LayerNorm backward
     const bool dx_is_bf16 = d->x_dtype == CRF_DT_BF16;
     float* dxo = i == 0 ? (dx_is_bf16 ? nullptr : static_cast<float*>(dx))
-                        : reinterpret_cast<float*>(Wk + W.mid_f32 + (i & 1) * align_up(T * C * 4));
+                        : reinterpret_cast<float*>(Wk + W.mid_f32[i & 1]);
     void* dxo16 = i == 0 ? (dx_is_bf16 ? dx : nullptr)
-                         : static_cast<void*>(Wk + W.mid_bf16 + (i & 1) * align_up(T * C * 2));
+                         : static_cast<void*>(Wk + W.mid_bf16[i & 1]);
     if (block_bwd_impl(&bd, a->params + i, xin, S + L.vb, g32, g16, S + L.blk[i], dxo, dxo16, dv,
                        i == a->depth - 1 ? 0 : 1, g + i, Wk + W.blk, bwd_layout(bd).total, stream))
       return 1;

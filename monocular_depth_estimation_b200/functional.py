@@ -19,6 +19,31 @@ PARAM_KEYS = ("norm1.weight", "norm1.bias", "attn.qk.weight", "attn.qk.bias", "a
               "mlp.fc2.weight", "mlp.fc2.bias")
 
 
+_GUARD = 4096
+
+
+def _guard_on():
+    """CRF_DEBUG_GUARD=1 (tests): every caller-allocated byte buffer gets a patterned tail that must survive the call --
+    the library's sub-allocations inside `saved` / workspace are checked for overruns this way."""
+    import os
+    return os.environ.get("CRF_DEBUG_GUARD", "0") == "1"
+
+
+def _alloc_bytes(nbytes, device):
+    if not _guard_on():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    buf = torch.empty(nbytes + _GUARD, dtype=torch.uint8, device=device)
+    buf[nbytes:].fill_(0xA5)
+    return buf
+
+
+def _check_guard(buf, nbytes, what):
+    if _guard_on() and buf.numel() == nbytes + _GUARD:
+        torch.cuda.synchronize(buf.device)
+        if not bool((buf[nbytes:] == 0xA5).all()):
+            raise RuntimeError(f"{what}: the library wrote past the end of a {nbytes}-byte buffer")
+
+
 def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -62,11 +87,12 @@ class _CRFBlockFn(torch.autograd.Function):
             desc = make_desc(B, H, W, Cd, num_heads, shift, window=window, training=training, device=dev.index,
                              x=xd, v=v_arg)
         saved_bytes, _, ws_bwd = _sizes(desc)
-        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        saved = _alloc_bytes(saved_bytes, dev)
         y = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
         ps = _param_struct(params, qk_scale, eps)
         L.check(L.lib().crf_block_fwd(C.byref(desc), C.byref(ps), xd.data_ptr(), v_arg.data_ptr(), y.data_ptr(),
                                       saved.data_ptr(), None, 0, _stream_ptr(dev)), "crf_block_fwd")
+        _check_guard(saved, saved_bytes, "crf_block_fwd saved")
         if training:
             ctx.save_for_backward(xd, v_arg, saved, *params)
             ctx.desc = desc
@@ -81,7 +107,7 @@ class _CRFBlockFn(torch.autograd.Function):
         dev = xd.device
         B, Ltok, Cd = xd.shape
         dy = dy.contiguous().float()
-        ws = torch.empty(ws_bwd, dtype=torch.uint8, device=dev)
+        ws = _alloc_bytes(ws_bwd, dev)
         dx = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
         dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
         # one zero-filled buffer, 13 views (256-byte aligned: the kernels store with 16-byte vectors and TMA)
@@ -97,7 +123,8 @@ class _CRFBlockFn(torch.autograd.Function):
         ps = _param_struct(params, qk_scale, eps)
         L.check(L.lib().crf_block_bwd(C.byref(desc), C.byref(ps), xd.data_ptr(), v_arg.data_ptr(), dy.data_ptr(),
                                       saved.data_ptr(), dx.data_ptr(), dv.data_ptr(), 0, C.byref(gs), ws.data_ptr(),
-                                      ws.numel(), _stream_ptr(dev)), "crf_block_bwd")
+                                      ws_bwd, _stream_ptr(dev)), "crf_block_bwd")
+        _check_guard(ws, ws_bwd, "crf_block_bwd workspace")
         return (dx, dv, None, None, None, None, None, None, None, None, *grads)
 
 
@@ -144,7 +171,7 @@ class _CRFLayerFn(torch.autograd.Function):
         sb, wb = C.c_size_t(), C.c_size_t()
         L.check(L.lib().crf_layer_sizes(C.byref(desc), depth, int(with_norm), C.byref(sb), C.byref(wb)),
                 "crf_layer_sizes")
-        saved = torch.empty(sb.value, dtype=torch.uint8, device=dev)
+        saved = _alloc_bytes(sb.value, dev)
         y = torch.empty(B, Ltok, Cd, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
         pa = (L.BlockParams * depth)()
         for i in range(depth):
@@ -157,6 +184,7 @@ class _CRFLayerFn(torch.autograd.Function):
                          nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None)
         L.check(L.lib().crf_layer_fwd(C.byref(desc), C.byref(la), xd.data_ptr(), v_arg.data_ptr(), y.data_ptr(),
                                       saved.data_ptr(), _stream_ptr(dev)), "crf_layer_fwd")
+        _check_guard(saved, sb.value, "crf_layer_fwd saved")
         if training:
             ctx.save_for_backward(xd, v_arg, saved, *((nw, nb) if with_norm else ()), *params)
             ctx.desc = desc
@@ -172,7 +200,7 @@ class _CRFLayerFn(torch.autograd.Function):
         desc, dev = ctx.desc, xd.device
         B, Ltok, Cd = xd.shape
         dy = dy.contiguous().to(torch.bfloat16 if out_bf16 else torch.float32)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = _alloc_bytes(ws_bytes, dev)
         dx = torch.empty(B, Ltok, Cd, dtype=xd.dtype, device=dev)   # in x's dtype: no autograd cast afterwards
         dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
         # one zero-filled buffer for every parameter gradient (256-byte aligned views)
@@ -195,7 +223,8 @@ class _CRFLayerFn(torch.autograd.Function):
         dnb = views[13 * depth + 1].data_ptr() if with_norm else None
         L.check(L.lib().crf_layer_bwd(C.byref(desc), C.byref(la), xd.data_ptr(), v_arg.data_ptr(), dy.data_ptr(),
                                       saved.data_ptr(), dx.data_ptr(), dv.data_ptr(), ga, dnw, dnb, ws.data_ptr(),
-                                      ws.numel(), _stream_ptr(dev)), "crf_layer_bwd")
+                                      ws_bytes, _stream_ptr(dev)), "crf_layer_bwd")
+        _check_guard(ws, ws_bytes, "crf_layer_bwd workspace")
         gn = (views[13 * depth], views[13 * depth + 1]) if with_norm else (None, None)
         return (dx, dv, None, None, None, None, None, None, None, None, gn[0], gn[1], *views[:13 * depth])
 

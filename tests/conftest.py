@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # every `saved` / workspace buffer the Python bridge hands to the library gets a patterned guard tail that is
+    # verified after the call (functional._check_guard): catches sub-allocation overruns inside the C library
+    os.environ.setdefault("CRF_DEBUG_GUARD", "1")
 
 
 def pytest_collection_modifyitems(config, items):
