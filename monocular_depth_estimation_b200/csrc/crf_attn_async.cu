@@ -725,6 +725,21 @@ attn_bwd_async_kernel(const AttnParams P) {
                             pack_bf16(__uint_as_float(b[8 * c + 4]), __uint_as_float(b[8 * c + 5])),
                             pack_bf16(__uint_as_float(b[8 * c + 6]), __uint_as_float(b[8 * c + 7])));
         warp_store_rows64<false>(scratch, lane, v, tq, dqb + C * 2, static_cast<int64_t>(C) * 4);  // dk
+        // zero-padded keys: k == bias, so their gradient goes to the k half of qk.bias (warp-reduced, one atomic/lane)
+        if (__any_sync(0xffffffffu, etok == -1)) {
+          float mine = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = warp_sum(etok == -1 ? __uint_as_float(b[j]) : 0.f);
+            if (lane == j) mine = s;
+          }
+          atomicAdd(P.d_qk_bias + C + h * HD + lane, mine);
+        }
+        // dv and dk are on their way (64 of the 96 result registers are dead): pre-load the bias and hand the TMEM
+        // columns back BEFORE the last store, so the next first-stage MMAs of this lane run under it
+        preload_bias(brow, pos, t0 + half * 64);
+        tc_fence_before();
+        mbar_arrive(bars.t_free(g));
         const float sc = P.scale;  // d(xW+b) = dq * scale because q was stored pre-scaled
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -734,19 +749,6 @@ attn_bwd_async_kernel(const AttnParams P) {
                             pack_bf16(sc * __uint_as_float(c2[8 * c + 6]), sc * __uint_as_float(c2[8 * c + 7])));
         warp_store_rows64<false>(scratch, lane, v, tq, dqb, static_cast<int64_t>(C) * 4);          // dq
       }
-      // zero-padded keys: k == bias, so their gradient goes to the k half of qk.bias (warp-reduced, one atomic/lane)
-      if (__any_sync(0xffffffffu, etok == -1)) {
-        float mine = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = warp_sum(etok == -1 ? __uint_as_float(b[j]) : 0.f);
-          if (lane == j) mine = s;
-        }
-        atomicAdd(P.d_qk_bias + C + h * HD + lane, mine);
-      }
-      preload_bias(brow, pos, t0 + half * 64);  // the next S of this lane accumulates on top of the bias
-      tc_fence_before();
-      mbar_arrive(bars.t_free(g));  // TMEM columns of this lane may be overwritten by the next S/dP
       CRF_PROF_MARK(6);
       rv = rv_next;
       lse = lse_next;

@@ -41,7 +41,9 @@ def check(c):
     xd = x.astype(np.float64)
     g_true = xd * 0.5 * (1 + erf(xd / np.sqrt(2)))
     dg_true = 0.5 * (1 + erf(xd / np.sqrt(2))) + xd * np.exp(-xd * xd / 2) / np.sqrt(2 * np.pi)
-    dg = cdf + x * np.float32(0.3989422804) * np.exp2(np.float32(-0.72134752) * x * x).astype(np.float32)
+    ln2 = np.float32(np.log(2.0))
+    wp = (np.float32(5) * c[2] * t + np.float32(3) * c[1]) * t + c[0]          # w'(x) of the fitted exponent
+    dg = cdf + x * cdf * (np.float32(1) - cdf) * wp * ln2                     # exact derivative of the sigmoid form
     return float(np.abs(x * cdf - g_true).max()), float(np.abs(dg - dg_true).max())
 
 
