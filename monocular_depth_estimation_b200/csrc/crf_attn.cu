@@ -10,14 +10,15 @@ int launch_attn_fwd_async(const AttnParams& P, const crf_block_desc& d, cudaStre
 int launch_attn_bwd_async(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
 
 int fill_attn_params(AttnParams& P, const crf_block_desc& d) {
-  CRF_CHECK(d.C % d.num_heads == 0 && d.C / d.num_heads == 32,
-            "attention core: head_dim must be 32 (C=%d, heads=%d)", d.C, d.num_heads);
+  CRF_CHECK(d.C % d.num_heads == 0 && (d.C / d.num_heads == 32 || d.C / d.num_heads == 16),
+            "attention core: head_dim must be 16 or 32 (C=%d, heads=%d)", d.C, d.num_heads);
   CRF_CHECK(d.window == 7, "attention core: window must be 7 (got %d)", d.window);
   CRF_CHECK(d.shift >= 0 && d.shift < d.window, "shift_size must in 0-window_size");
   P.gm = WindowGeom(d.H, d.W, d.window, d.shift);
   P.B = d.B;
   P.C = d.C;
   P.nH = d.num_heads;
+  P.hd = d.C / d.num_heads;
   P.total_windows = d.B * P.gm.nW;
   P.npairs = (P.total_windows + 1) / 2;
   P.rcp_nW = 1.0f / static_cast<float>(P.gm.nW);

@@ -201,12 +201,13 @@ __device__ __forceinline__ void load_chunk(const AttnParams& P, int tok, int r, 
                                            uint8_t* in_g, bool& any_async) {
   const int C = P.C;
   const uint32_t off = sw64_offset(r, c);
-  if (tok >= 0) {
-    const __nv_bfloat16* qrow = P.qk + static_cast<int64_t>(tok) * 2 * C + h * HD + 8 * c;
+  const bool live_c = 8 * c < P.hd;  // head_dim 16: chunks 2, 3 of the 32-wide tiles stay zero
+  if (tok >= 0 && live_c) {
+    const __nv_bfloat16* qrow = P.qk + static_cast<int64_t>(tok) * 2 * C + h * P.hd + 8 * c;
     cp_async16(in_s + off, qrow);
     cp_async16(in_s + 8192 + off, qrow + C);
-    cp_async16(in_s + 16384 + off, P.vb + static_cast<int64_t>(tok) * C + h * HD + 8 * c);
-    if (BWD) cp_async16(in_s + 24576 + off, P.dout + static_cast<int64_t>(tok) * C + h * HD + 8 * c);
+    cp_async16(in_s + 16384 + off, P.vb + static_cast<int64_t>(tok) * C + h * P.hd + 8 * c);
+    if (BWD) cp_async16(in_s + 24576 + off, P.dout + static_cast<int64_t>(tok) * C + h * P.hd + 8 * c);
     any_async = true;
   } else {
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -214,8 +215,8 @@ __device__ __forceinline__ void load_chunk(const AttnParams& P, int tok, int r, 
     *reinterpret_cast<uint4*>(in_g + 16384 + off) = z;
     if (BWD) *reinterpret_cast<uint4*>(in_g + 24576 + off) = z;
     uint4 kv = z;
-    if (tok == -1) {  // zero-padded token: k = bias (LayerNorm'd zero row through qk), v = 0
-      const float* bk = P.qk_bias + C + h * HD + 8 * c;
+    if (tok == -1 && live_c) {  // zero-padded token: k = bias (LayerNorm'd zero row through qk), v = 0
+      const float* bk = P.qk_bias + C + h * P.hd + 8 * c;
       const float4 a = __ldg(reinterpret_cast<const float4*>(bk));
       const float4 b = __ldg(reinterpret_cast<const float4*>(bk + 4));
       kv = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
@@ -270,7 +271,7 @@ __device__ __forceinline__ void loader_loop(const AttnParams& P, const Bars& bar
 // (lane >> 2) + 8 k (< 0: not stored).  RED: fp32 accumulate with red.global.add.v4.f32.
 template <bool RED>
 __device__ __forceinline__ void warp_store_rows64(uint8_t* scratch, int lane, const uint4 (&v)[4], const int (&tokq)[4],
-                                                  uint8_t* gbase, int64_t row_bytes) {
+                                                  uint8_t* gbase, int64_t row_bytes, int nchunks = 4) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(scratch + lane * 80 + 16 * c) = v[c];
   __syncwarp();
@@ -278,7 +279,7 @@ __device__ __forceinline__ void warp_store_rows64(uint8_t* scratch, int lane, co
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const uint4 d = *reinterpret_cast<const uint4*>(scratch + ((lane >> 2) + 8 * k) * 80 + 16 * c);
-    if (tokq[k] >= 0) {
+    if (tokq[k] >= 0 && c < nchunks) {
       uint8_t* dst = gbase + static_cast<int64_t>(tokq[k]) * row_bytes + 16 * c;
       if (RED)
         red_add_f32x4(reinterpret_cast<float*>(dst), make_float4(__uint_as_float(d.x), __uint_as_float(d.y),
@@ -470,8 +471,8 @@ attn_fwd_async_kernel(const AttnParams P) {
         int tq[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) tq[k] = __shfl_sync(0xffffffffu, rv.tok, (lane >> 2) + 8 * k);
-        warp_store_rows64<false>(scratch, lane, v, tq, reinterpret_cast<uint8_t*>(P.o) + h * HD * 2,
-                                 static_cast<int64_t>(C) * 2);
+        warp_store_rows64<false>(scratch, lane, v, tq, reinterpret_cast<uint8_t*>(P.o) + h * P.hd * 2,
+                                 static_cast<int64_t>(C) * 2, P.hd / 8);
       }
       rv = rv_next;
     }
@@ -709,22 +710,23 @@ attn_bwd_async_kernel(const AttnParams P) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) tq[k] = __shfl_sync(0xffffffffu, etok, (lane >> 2) + 8 * k);
         uint4 v[4];
-        uint8_t* dvb = reinterpret_cast<uint8_t*>(P.dv) + h * HD * 4;
+        uint8_t* dvb = reinterpret_cast<uint8_t*>(P.dv) + h * P.hd * 4;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {  // dv: 128 bytes per row, two 64-byte passes
+        for (int hf = 0; hf < 2; ++hf) {  // dv: 4 * head_dim bytes per row, 64-byte passes
+          if (16 * hf >= P.hd) break;
 #pragma unroll
           for (int c = 0; c < 4; ++c) v[c] = make_uint4(a[16 * hf + 4 * c], a[16 * hf + 4 * c + 1], a[16 * hf + 4 * c + 2], a[16 * hf + 4 * c + 3]);
           if (P.dv_acc) warp_store_rows64<true>(scratch, lane, v, tq, dvb + 64 * hf, static_cast<int64_t>(C) * 4);
           else warp_store_rows64<false>(scratch, lane, v, tq, dvb + 64 * hf, static_cast<int64_t>(C) * 4);
         }
-        uint8_t* dqb = reinterpret_cast<uint8_t*>(P.dqk) + h * HD * 2;
+        uint8_t* dqb = reinterpret_cast<uint8_t*>(P.dqk) + h * P.hd * 2;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           v[c] = make_uint4(pack_bf16(__uint_as_float(b[8 * c]), __uint_as_float(b[8 * c + 1])),
                             pack_bf16(__uint_as_float(b[8 * c + 2]), __uint_as_float(b[8 * c + 3])),
                             pack_bf16(__uint_as_float(b[8 * c + 4]), __uint_as_float(b[8 * c + 5])),
                             pack_bf16(__uint_as_float(b[8 * c + 6]), __uint_as_float(b[8 * c + 7])));
-        warp_store_rows64<false>(scratch, lane, v, tq, dqb + C * 2, static_cast<int64_t>(C) * 4);  // dk
+        warp_store_rows64<false>(scratch, lane, v, tq, dqb + C * 2, static_cast<int64_t>(C) * 4, P.hd / 8);  // dk
         // zero-padded keys: k == bias, so their gradient goes to the k half of qk.bias (warp-reduced, one atomic/lane)
         if (__any_sync(0xffffffffu, etok == -1)) {
           float mine = 0.f;
@@ -733,7 +735,7 @@ attn_bwd_async_kernel(const AttnParams P) {
             const float s = warp_sum(etok == -1 ? __uint_as_float(b[j]) : 0.f);
             if (lane == j) mine = s;
           }
-          atomicAdd(P.d_qk_bias + C + h * HD + lane, mine);
+          if (lane < P.hd) atomicAdd(P.d_qk_bias + C + h * P.hd + lane, mine);
         }
         // dv and dk are on their way (64 of the 96 result registers are dead): pre-load the bias and hand the TMEM
         // columns back BEFORE the last store, so the next first-stage MMAs of this lane run under it
@@ -747,7 +749,7 @@ attn_bwd_async_kernel(const AttnParams P) {
                             pack_bf16(sc * __uint_as_float(c2[8 * c + 2]), sc * __uint_as_float(c2[8 * c + 3])),
                             pack_bf16(sc * __uint_as_float(c2[8 * c + 4]), sc * __uint_as_float(c2[8 * c + 5])),
                             pack_bf16(sc * __uint_as_float(c2[8 * c + 6]), sc * __uint_as_float(c2[8 * c + 7])));
-        warp_store_rows64<false>(scratch, lane, v, tq, dqb, static_cast<int64_t>(C) * 4);          // dq
+        warp_store_rows64<false>(scratch, lane, v, tq, dqb, static_cast<int64_t>(C) * 4, P.hd / 8);  // dq
       }
       CRF_PROF_MARK(6);
       rv = rv_next;

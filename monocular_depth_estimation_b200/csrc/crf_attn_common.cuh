@@ -12,6 +12,7 @@ constexpr int kNTok = 49;
 struct AttnParams {
   WindowGeom gm;
   int B, C, nH;
+  int hd;             // head_dim: 32, or 16 (tiles stay 32 wide, the upper half zero-filled)
   int total_windows;  // B * nW
   int npairs;
   const __nv_bfloat16* qk;   // (T, 2C)

@@ -15,8 +15,8 @@ def load_golden(name):
 
 def rel_l2(a, b):
     """||a - b||_2 / ||b||_2 in float64 -- the 'rel' of BASELINE.json's tolerances."""
-    a = torch.as_tensor(a).double().cpu()
-    b = torch.as_tensor(b).double().cpu()
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 

@@ -192,6 +192,13 @@ def test_config2_stage_shapes_vs_oracle(H, W, C, nH, shift):
     _run_block_vs_oracle(8, H, W, C, nH, shift, seed=100 + C + shift, strided=True, oracle_device=DEV)
 
 
+@pytest.mark.parametrize("H,W,C,nH,shift", [(9, 10, 64, 4, 3), (30, 40, 128, 8, 0), (15, 20, 256, 16, 3), (30, 40, 512, 32, 3)])
+def test_head_dim_16_block_vs_oracle(H, W, C, nH, shift):
+    """BASELINE.json configs[2] sweeps heads 4-32 at embed 64-512: the head_dim = 16 points (the attention tiles stay
+    32 wide, the upper half zero-filled)."""
+    _run_block_vs_oracle(2, H, W, C, nH, shift, seed=300 + C + shift, strided=True, oracle_device=DEV)
+
+
 def test_inference_path_matches_training_path():
     pkg = _pkg()
     torch.manual_seed(0)
@@ -376,10 +383,10 @@ def test_c_api_rejects_bad_arguments():
     d = ops.make_desc(1, 7, 7, 64, 2, 0, device=0)
     assert lib.crf_block_fwd(C.byref(d), None, None, None, None, None, None, 0, None) != 0
     assert b"null pointer" in lib.crf_last_error()
-    d.num_heads = 4  # head_dim 16: not implemented
+    d.num_heads = 1  # head_dim 64: not implemented
     s = C.c_size_t()
     assert lib.crf_block_sizes(C.byref(d), C.byref(s), None, None) != 0
-    assert b"head_dim must be 32" in lib.crf_last_error()
+    assert b"head_dim must be 16 or 32" in lib.crf_last_error()
     a = _lib.GemmArgs()
     x = torch.zeros(128, 64, dtype=torch.bfloat16, device=DEV)
     a.A, a.B, a.out0 = x.data_ptr(), x.data_ptr(), x.data_ptr()

@@ -312,7 +312,8 @@ def _attn_reference(qk, vb, qk_bias, table, B, H, W, C, nH, shift):
 
 
 ATTN_CASES = [(1, 7, 7, 64, 2, 0), (1, 14, 14, 64, 2, 0), (2, 9, 10, 64, 2, 0), (2, 9, 10, 64, 2, 3),
-              (1, 15, 20, 128, 4, 3), (3, 30, 40, 128, 4, 3), (2, 15, 20, 256, 8, 0), (1, 21, 16, 1024, 32, 3)]
+              (1, 15, 20, 128, 4, 3), (3, 30, 40, 128, 4, 3), (2, 15, 20, 256, 8, 0), (1, 21, 16, 1024, 32, 3),
+              (2, 9, 10, 64, 4, 3), (1, 15, 20, 128, 8, 0)]   # the last two: head_dim 16
 
 
 @pytest.mark.parametrize("B,H,W,C,nH,shift", ATTN_CASES)
