@@ -268,11 +268,34 @@ def run_ours(args):
             step_eager()
 
     last_loss = [0.0]
+    # End-to-end input pipeline (what a pinned-memory loader with prefetch does): every step's image + depth are copied
+    # host -> device from pinned memory on a copy stream into a staging pair while the PREVIOUS step computes; the step
+    # itself starts with a device-to-device move into the graph's static input tensors.  The first step of a timed
+    # region copies its own batch un-overlapped, so K steps make exactly K host -> device copies, all consumed.
+    copy_stream = torch.cuda.Stream()
+    image_s, depth_s = torch.empty_like(image_d), torch.empty_like(depth_d)
+    ev_h2d, ev_d2d = torch.cuda.Event(), torch.cuda.Event()
+    e2e_k = [0]
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_d2d)          # the staging pair has been consumed
+            image_s.copy_(image_h, non_blocking=True)
+            depth_s.copy_(depth_h, non_blocking=True)
+            ev_h2d.record(copy_stream)
 
     def step_e2e():
-        if graph is not None:  # the graph reads its inputs from image_d / depth_d: refill them from pinned host memory
-            image_d.copy_(image_h, non_blocking=True)
-            depth_d.copy_(depth_h, non_blocking=True)
+        if graph is not None:  # the graph reads its inputs from image_d / depth_d
+            cur = torch.cuda.current_stream()
+            if e2e_k[0] % args.steps == 0:
+                prefetch()                          # first step of a region: its own batch, not overlapped
+            cur.wait_event(ev_h2d)
+            image_d.copy_(image_s, non_blocking=True)
+            depth_d.copy_(depth_s, non_blocking=True)
+            ev_d2d.record(cur)
+            if (e2e_k[0] + 1) % args.steps != 0:
+                prefetch()                          # next step's batch travels while this step computes
+            e2e_k[0] += 1
             graph.replay()
             last_loss[0] = float(static_loss.item())
         else:
@@ -299,7 +322,8 @@ def run_ours(args):
         launches = launches_per_replay * args.steps  # replayed from the graph: counted once at capture time
     clocks = sampler.stop() if rank == 0 else None
 
-    step_e2e()
+    for _ in range(args.steps):   # one full untimed region (keeps the prefetch phase aligned with the step counter)
+        step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
     # per-kernel timing pass: same step loop, every library kernel bracketed by CUDA events on its own stream
@@ -450,7 +474,10 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": image_h.numel() * 4 + depth_h.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss[0]},
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss[0],
+                "input_pipeline": ("pinned host -> staging copy of step i+1 on a copy stream while step i computes "
+                                   "(K copies for K steps, the first one not overlapped); loss read back every step")
+                if graph is not None else "copies and step on one stream"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "kernel_breakdown": breakdown[:8],
