@@ -128,11 +128,33 @@ def index_case(ref, name):
     print(name, "ok")
 
 
+def loss_case(name):
+    """The training loss exactly as the reference computes it (src/train.py:94-100: l1_criterion = nn.L1Loss(),
+    ssim = loss.SSIM(), loss = 1.0 * ssim + 0.1 * l1) on small maps, forward value and d loss / d prediction."""
+    sys.path.insert(0, REF_SRC)
+    import loss as ref_loss
+    gen = torch.Generator().manual_seed(5)
+    blob = {}
+    for tag, shape in (("a", (2, 1, 11, 13)), ("b", (1, 1, 2, 2)), ("c", (3, 1, 3, 7))):
+        pred = torch.rand(shape, generator=gen)
+        tgt = (0.5 * pred + 0.5 * torch.rand(shape, generator=gen)).clamp(0, 1)
+        tgt[..., : shape[-1] // 2] = pred[..., : shape[-1] // 2]   # SSIM = 1 there: the clamp's lower boundary
+        pred = pred.detach().requires_grad_(True)
+        val = 1.0 * ref_loss.SSIM()(pred, tgt) + 0.1 * nn.L1Loss()(pred, tgt)
+        val.backward()
+        blob[f"pred.{tag}"], blob[f"target.{tag}"] = pred.detach().numpy(), tgt.numpy()
+        blob[f"loss.{tag}"] = np.array([float(val.detach())], dtype=np.float64)
+        blob[f"dpred.{tag}"] = pred.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+    print(name, "ok")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref = import_reference()
     index_case(ref, "index_maps")
+    loss_case("loss_ssim_l1")
     # (a) both blocks (shift 0 and 3), both dims padded, strided NCHW-view inputs like NewCRF.forward produces
     layer_case(ref, "layer_9x10_c64", B=2, H=9, W=10, C=64, nH=2, depth=2, seed=1, strided=True)
     # (b) decoder scale 1/32 geometry (15x20 -> 21x21) with contiguous inputs

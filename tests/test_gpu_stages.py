@@ -240,6 +240,19 @@ def test_pixel_shuffle_nhwc_bit_exact(shape, dtype):
     assert torch.equal(x.grad, F.pixel_unshuffle(g, 2))
 
 
+def test_depth_loss_matches_reference_golden():
+    """The fused loss kernels against the golden value / gradient of the unmodified reference loss."""
+    from monocular_depth_estimation_b200 import functional as CF
+    g = load_golden("loss_ssim_l1")
+    for tag in ("a", "b", "c"):
+        pred = torch.from_numpy(g[f"pred.{tag}"]).to(DEV).requires_grad_(True)
+        val = CF.depth_loss(pred, torch.from_numpy(g[f"target.{tag}"]).to(DEV))
+        val.backward()
+        assert abs(float(val.detach()) - float(g[f"loss.{tag}"][0])) < 2e-5
+        _check(pred.grad.reshape(-1, pred.shape[-1]), torch.from_numpy(g[f"dpred.{tag}"]).to(DEV).reshape(-1, pred.shape[-1]),
+               2e-4, f"depth_loss d pred ({tag})")
+
+
 def test_colsum_cast_convert():
     ops = _ops()
     gq = _rand_bf16(1234, 384, seed=11)

@@ -54,3 +54,19 @@ def test_layer_forward_backward_matches_reference(name):
     for i, p in enumerate(blocks):
         for k, t in p.items():
             assert rel_l2(t.grad, g[f"grad.blocks.{i}.{k}"]) < 2e-5, (i, k)
+
+
+def test_loss_matches_reference_golden():
+    """oracle.model_oracle.ssim_l1_loss (and the host-side composition in training.py) against the value and gradient
+    the unmodified reference loss produced (loss.SSIM + nn.L1Loss as combined at train.py:94-100)."""
+    import torch
+    from monocular_depth_estimation_b200 import training as TR
+    from oracle import model_oracle as MO
+    g = load_golden("loss_ssim_l1")
+    for tag in ("a", "b", "c"):
+        for fn in (MO.ssim_l1_loss, TR.depth_loss):
+            pred = torch.from_numpy(g[f"pred.{tag}"]).requires_grad_(True)
+            val = fn(pred, torch.from_numpy(g[f"target.{tag}"]))
+            val.backward()
+            assert abs(float(val.detach()) - float(g[f"loss.{tag}"][0])) < 1e-6
+            assert rel_l2(pred.grad, g[f"dpred.{tag}"]) < 1e-5
