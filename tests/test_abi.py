@@ -50,3 +50,30 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.BlockDesc) == 12 * 4 + 7 * 8
     assert ctypes.sizeof(_lib.BlockParams) == 13 * 8 + 8
     assert ctypes.sizeof(_lib.BlockGrads) == 13 * 8
+
+
+def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
+    """Compile a tiny C program against include/crf_sm100.h (gcc) that prints sizeof and every offsetof, and compare
+    with the ctypes mirrors in _lib.py -- a silent mismatch here would corrupt arguments at the drop-in boundary."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"crf_block_desc": _lib.BlockDesc, "crf_block_params": _lib.BlockParams,
+               "crf_block_grads": _lib.BlockGrads, "crf_layer_args": _lib.LayerArgs, "crf_gemm_args": _lib.GemmArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "crf_sm100.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
