@@ -8,10 +8,21 @@ namespace crf {
 
 int launch_attn_fwd_async(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
 int launch_attn_bwd_async(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
+int launch_attn_fwd_wide(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);  // crf_attn_wide.cu
+int launch_attn_bwd_wide(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
+
+// head_dim 16 / 32: crf_attn_async.cu.  head_dim 64 / 128 (crf_attn_wide.cu) has not run on hardware yet and is
+// therefore opt-in: CRF_WIDE_HEADS=1.
+bool head_dim_supported(int hd) {
+  if (hd == 16 || hd == 32) return true;
+  static const bool wide = getenv("CRF_WIDE_HEADS") != nullptr && atoi(getenv("CRF_WIDE_HEADS")) != 0;
+  return wide && (hd == 64 || hd == 128);
+}
 
 int fill_attn_params(AttnParams& P, const crf_block_desc& d) {
-  CRF_CHECK(d.C % d.num_heads == 0 && (d.C / d.num_heads == 32 || d.C / d.num_heads == 16),
-            "attention core: head_dim must be 16 or 32 (C=%d, heads=%d)", d.C, d.num_heads);
+  CRF_CHECK(d.num_heads > 0 && d.C % d.num_heads == 0 && head_dim_supported(d.C / d.num_heads),
+            "attention core: head_dim must be 16 or 32 (C=%d, heads=%d; 64 / 128: experimental, CRF_WIDE_HEADS=1)", d.C,
+            d.num_heads);
   CRF_CHECK(d.window == 7, "attention core: window must be 7 (got %d)", d.window);
   CRF_CHECK(d.shift >= 0 && d.shift < d.window, "shift_size must in 0-window_size");
   P.gm = WindowGeom(d.H, d.W, d.window, d.shift);
@@ -41,7 +52,7 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.ext_mask_nw = ext_mask_nw > 0 ? ext_mask_nw : 1;
   P.o = reinterpret_cast<__nv_bfloat16*>(o);
   P.lse = lse;
-  return launch_attn_fwd_async(P, d, st);
+  return P.hd > 32 ? launch_attn_fwd_wide(P, d, st) : launch_attn_fwd_async(P, d, st);
 }
 
 int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
@@ -63,7 +74,7 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.dv_acc = dv_acc;
   P.d_table = d_table;
   P.d_qk_bias = d_qk_bias;
-  return launch_attn_bwd_async(P, d, st);
+  return P.hd > 32 ? launch_attn_bwd_wide(P, d, st) : launch_attn_bwd_async(P, d, st);
 }
 
 }  // namespace crf

@@ -199,6 +199,15 @@ def test_head_dim_16_block_vs_oracle(H, W, C, nH, shift):
     _run_block_vs_oracle(2, H, W, C, nH, shift, seed=300 + C + shift, strided=True, oracle_device=DEV)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("CRF_WIDE_HEADS") != "1",
+                    reason="head_dim 64/128 is opt-in: CRF_WIDE_HEADS=1 (tests/test_zz_gpu_wide_heads.py)")
+@pytest.mark.parametrize("H,W,C,nH,shift", [(9, 10, 64, 1, 3), (30, 40, 128, 2, 0), (15, 20, 256, 4, 3), (15, 20, 256, 2, 0),
+                                            (30, 40, 512, 8, 3), (16, 23, 512, 4, 3)])
+def test_wide_head_block_vs_oracle(H, W, C, nH, shift):
+    """BASELINE.json configs[2], the head_dim = 64 and 128 points (crf_attn_wide.cu: 32-wide slices of a head)."""
+    _run_block_vs_oracle(2, H, W, C, nH, shift, seed=400 + C + shift, strided=True, oracle_device=DEV)
+
+
 def test_inference_path_matches_training_path():
     pkg = _pkg()
     torch.manual_seed(0)
