@@ -3,6 +3,7 @@
 so the outputs are committed as small .npz files and this script documents how they were made.
 
     python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py layer_8x13_c64_hd64 ...   # only the named fixtures
 
 `timm` is not installed; the reference imports three trivial symbols from it that are only used at construction
 time with rate 0 (newcrf_layers.py:6,107,184,187), so a stub module is injected.
@@ -153,14 +154,26 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref = import_reference()
-    index_case(ref, "index_maps")
-    loss_case("loss_ssim_l1")
-    # (a) both blocks (shift 0 and 3), both dims padded, strided NCHW-view inputs like NewCRF.forward produces
-    layer_case(ref, "layer_9x10_c64", B=2, H=9, W=10, C=64, nH=2, depth=2, seed=1, strided=True)
-    # (b) decoder scale 1/32 geometry (15x20 -> 21x21) with contiguous inputs
-    layer_case(ref, "layer_15x20_c64", B=1, H=15, W=20, C=64, nH=2, depth=2, seed=2, strided=False)
-    # (c) no padding at all (14x21), C=128 / 4 heads (config-1 channel geometry), single unshifted block
-    layer_case(ref, "block_14x21_c128", B=1, H=14, W=21, C=128, nH=4, depth=1, seed=3, strided=False)
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
+    if want("index_maps"):
+        index_case(ref, "index_maps")
+    if want("loss_ssim_l1"):
+        loss_case("loss_ssim_l1")
+    cases = [
+        # (a) both blocks (shift 0 and 3), both dims padded, strided NCHW-view inputs like NewCRF.forward produces
+        dict(name="layer_9x10_c64", B=2, H=9, W=10, C=64, nH=2, depth=2, seed=1, strided=True),
+        # (b) decoder scale 1/32 geometry (15x20 -> 21x21) with contiguous inputs
+        dict(name="layer_15x20_c64", B=1, H=15, W=20, C=64, nH=2, depth=2, seed=2, strided=False),
+        # (c) no padding at all (14x21), C=128 / 4 heads (config-1 channel geometry), single unshifted block
+        dict(name="block_14x21_c128", B=1, H=14, W=21, C=128, nH=4, depth=1, seed=3, strided=False),
+        # (d), (e) BASELINE configs[2] head widths other than 32: one 64-wide head, four 16-wide heads
+        dict(name="layer_8x13_c64_hd64", B=1, H=8, W=13, C=64, nH=1, depth=2, seed=4, strided=True),
+        dict(name="layer_8x13_c64_hd16", B=1, H=8, W=13, C=64, nH=4, depth=2, seed=6, strided=True),
+    ]
+    for c in cases:
+        if want(c["name"]):
+            layer_case(ref, **c)
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LAYER_CASES = ["layer_9x10_c64", "layer_15x20_c64", "block_14x21_c128"]
+HEAD_CASES = ["layer_8x13_c64_hd64", "layer_8x13_c64_hd16"]   # head widths other than 32 (BASELINE configs[2])
 
 
 def load_golden(name):

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import crf_oracle as O
-from tests.helpers import LAYER_CASES, golden_layer_inputs, load_golden, rel_l2
+from tests.helpers import HEAD_CASES, LAYER_CASES, golden_layer_inputs, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-2
@@ -35,6 +35,14 @@ def _layer_from_golden(g, C, nH, depth):
     missing, unexpected = layer.load_state_dict(sd, strict=True)   # drop-in: reference checkpoint keys load as-is
     assert not missing and not unexpected
     return layer.to(DEV)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CRF_WIDE_HEADS") != "1",
+                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_wide_heads.py (CRF_WIDE_HEADS=1)")
+@pytest.mark.parametrize("name", HEAD_CASES)
+def test_head_width_golden(name):
+    """The reference's own outputs / gradients for one 64-wide head and for four 16-wide heads."""
+    test_layer_matches_reference_golden(name)
 
 
 @pytest.mark.parametrize("name", LAYER_CASES)

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import crf_oracle as O
-from tests.helpers import LAYER_CASES, golden_layer_inputs, load_golden, rel_l2
+from tests.helpers import HEAD_CASES, LAYER_CASES, golden_layer_inputs, load_golden, rel_l2
 
 
 def test_index_maps_bit_exact():
@@ -37,7 +37,7 @@ def test_known_answer_facts():
     assert O.padded_size(120, 7) == 126 and O.padded_size(160, 7) == 161
 
 
-@pytest.mark.parametrize("name", LAYER_CASES)
+@pytest.mark.parametrize("name", LAYER_CASES + HEAD_CASES)
 def test_layer_forward_backward_matches_reference(name):
     g = load_golden(name)
     (B, H, W, C, nH, depth), x, v, blocks = golden_layer_inputs(g)

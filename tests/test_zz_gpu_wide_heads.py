@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.xfail(strict=False, reason="head_dim 64/128 kernels not yet verified on hardware (opt-in: CRF_WIDE_HEADS=1)")
-@pytest.mark.parametrize("select", ["test_attn_fwd_wide", "test_attn_bwd_wide", "test_wide_head_block_vs_oracle"])
+@pytest.mark.parametrize("select", ["test_attn_fwd_wide", "test_attn_bwd_wide", "test_wide_head_block_vs_oracle",
+                                    "test_head_width_golden"])
 def test_wide_heads_isolated(select):
     env = dict(os.environ, CRF_WIDE_HEADS="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_stages.py", "tests/test_gpu_block.py", "-q", "-x",
