@@ -41,7 +41,7 @@ def _data(n):
     return torch.rand(n, 3, 9, 10, generator=g), torch.rand(n, 1, 9, 10, generator=g)
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, grad_dtype=None):
     os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
                        "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
     torch.set_num_threads(1)
@@ -49,7 +49,7 @@ def _worker(rank, world, port, out_path):
     assert (r, w, device.type) == (rank, world, "cpu")
     torch.manual_seed(0)
     model = _TinyDepthNet()
-    net = T.wrap_ddp(model, device, w)
+    net = T.wrap_ddp(model, device, w, grad_dtype=grad_dtype)
     img, dep = _data(4)
     shard = slice(rank * 2, rank * 2 + 2)                     # batch-sharded: whole images per rank
     loss = T.depth_loss(net(img[shard]), dep[shard])
@@ -72,6 +72,24 @@ def test_ddp_gradients_equal_full_batch_gradients(tmp_path):
     loss.backward()
     for k, p in model.named_parameters():
         assert torch.allclose(got[k], p.grad, rtol=1e-4, atol=1e-6), k
+
+
+def test_ddp_bf16_gradient_exchange(tmp_path):
+    """Optional bf16 bucket exchange (wrap_ddp(grad_dtype=torch.bfloat16)): same averaged gradients up to the bf16
+    rounding of the exchanged values."""
+    out = str(tmp_path / "grads_bf16.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, torch.bfloat16), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = _TinyDepthNet()
+    img, dep = _data(4)
+    loss = 0.5 * (T.depth_loss(model(img[:2]), dep[:2]) + T.depth_loss(model(img[2:]), dep[2:]))
+    loss.backward()
+    for k, p in model.named_parameters():
+        assert got[k].dtype == torch.float32
+        err = float((got[k] - p.grad).norm() / p.grad.norm().clamp_min(1e-30))
+        assert err < 1e-2, (k, err)
+    assert any(not torch.equal(got[k], p.grad) for k, p in model.named_parameters())   # the hook really ran
 
 
 def test_loss_matches_oracle_loss():
