@@ -150,6 +150,43 @@ def loss_case(name):
     print(name, "ok")
 
 
+def model_case(name):
+    """The reference's whole model (src/model_mobileV3_large_newCRFs.py: torchvision MobileNetV3-large encoder + NeWCRFs
+    decoder), unmodified, eval mode, on a small image: depth map, loss as in train.py:89-100, gradients of the image and
+    of a dozen small parameters.  Weights come from tests.helpers.fill_by_name (seeded by parameter NAME), so the oracle
+    and the product rebuild exactly the same model without a checkpoint.  Import shims:
+    matplotlib is absent (utils.py imports it for colour maps only) and `pretrained=True` needs the network."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests.helpers import MODEL_GRAD_KEYS, fill_by_name
+    for m in ("matplotlib", "matplotlib.cm"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    import torchvision.models as tvm
+    orig = tvm.mobilenet_v3_large
+    tvm.mobilenet_v3_large = lambda *a, **k: orig(weights=None)
+    try:
+        import model_mobileV3_large_newCRFs as ref_model
+        import loss as ref_loss
+        from utils import DepthNorm
+        model = ref_model.PTModel()
+    finally:
+        tvm.mobilenet_v3_large = orig
+    fill_by_name(model).eval()
+    gen = torch.Generator().manual_seed(11)
+    image = torch.rand(2, 3, 64, 96, generator=gen).requires_grad_(True)
+    depth = torch.rand(2, 1, 64, 96, generator=gen) * 9.0 + 1.0
+    pred = model(image)
+    val = 1.0 * ref_loss.SSIM()(pred, DepthNorm(depth)) + 0.1 * nn.L1Loss()(pred, DepthNorm(depth))
+    val.backward()
+    params = dict(model.named_parameters())
+    blob = {"image": image.detach().numpy(), "depth": depth.numpy(), "pred": pred.detach().numpy(),
+            "loss": np.array([float(val.detach())], dtype=np.float64), "dimage": image.grad.numpy(),
+            "keys": np.array(sorted(model.state_dict().keys()))}
+    for k in MODEL_GRAD_KEYS:
+        blob["grad." + k] = params[k].grad.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+    print(name, "pred", tuple(pred.shape), "mean", float(pred.mean()), "std", float(pred.std()), "loss", float(val))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -174,6 +211,8 @@ def main():
     for c in cases:
         if want(c["name"]):
             layer_case(ref, **c)
+    if want("model_64x96"):
+        model_case("model_64x96")
 
 
 if __name__ == "__main__":

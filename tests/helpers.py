@@ -41,3 +41,39 @@ def golden_layer_inputs(g, device="cpu"):
         blocks.append({k[len(pre):]: torch.from_numpy(t).to(device) for k, t in g.items()
                        if k.startswith(pre) and not k.endswith("relative_position_index")})
     return (B, H, W, C, nH, depth), x, v, blocks
+
+
+def fill_by_name(module):
+    """Deterministic, construction-order-independent values for every parameter and BatchNorm statistic of a model:
+    each tensor is drawn from a generator seeded by the CRC32 of its state_dict name.  The reference model (in the build
+    container, tests/golden/make_golden.py), the oracle model and the product model therefore get identical weights
+    from their NAMES alone -- no 180 MB checkpoint has to travel to the GPU box."""
+    import zlib
+    with torch.no_grad():
+        for name, t in list(module.named_parameters()) + list(module.named_buffers()):
+            if name.endswith("relative_position_index") or name.endswith("num_batches_tracked"):
+                continue
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+            r = torch.randn(t.shape, generator=g)
+            if name.endswith("running_var"):
+                t.copy_(1.0 + 0.2 * r.abs())
+            elif name.endswith("running_mean"):
+                t.copy_(0.1 * r)
+            elif name.endswith("relative_position_bias_table"):
+                t.copy_(0.2 * r)
+            elif t.dim() >= 2:                      # conv / linear weights: He scaling keeps activations O(1)
+                t.copy_(r * (2.0 / t[0].numel()) ** 0.5)
+            elif name.endswith("weight"):           # LayerNorm / BatchNorm scales
+                t.copy_(1.0 + 0.1 * r)
+            else:                                   # biases
+                t.copy_(0.1 * r)
+    return module
+
+
+# parameters whose gradients the full-model fixture stores (small tensors spread over encoder, bridge, every stage, head)
+MODEL_GRAD_KEYS = ["Unet.0.original_model.features.0.0.weight", "Unet.1.conv0.bias", "Unet.1.conv1.weight",
+                   "Unet.1.crf3.norm_crf.weight", "Unet.1.crf3.crf_layer.blocks.1.attn.relative_position_bias_table",
+                   "Unet.1.crf2.crf_layer.blocks.0.attn.qk.bias", "Unet.1.crf2.proj_v.bias",
+                   "Unet.1.crf1.crf_layer.blocks.1.mlp.fc2.bias", "Unet.1.crf1.norm_crf.bias",
+                   "Unet.1.crf0.crf_layer.blocks.0.norm1.weight", "Unet.1.crf0.crf_layer.blocks.1.attn.proj.bias",
+                   "Unet.1.crf0.proj_x.bias"]

@@ -282,6 +282,31 @@ def test_full_model_dropin_matches_oracle_model():
     assert err < TOL, err
 
 
+@pytest.mark.skipif(__import__("os").environ.get("CRF_WIDE_HEADS") != "1",
+                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_wide_heads.py (CRF_WIDE_HEADS=1)")
+def test_full_model_matches_reference_model_golden():
+    """The product model against the UNMODIFIED reference model's own numbers (tests/golden/model_64x96.npz: name-seeded
+    weights, eval mode): depth map, loss, image gradient, parameter gradients across encoder, bridge, stages and head."""
+    from monocular_depth_estimation_b200 import training as TR
+    from monocular_depth_estimation_b200.model import PTModel
+    from tests.helpers import MODEL_GRAD_KEYS, fill_by_name
+    g = load_golden("model_64x96")
+    model = fill_by_name(PTModel()).eval().to(DEV)
+    image = torch.from_numpy(g["image"]).to(DEV).requires_grad_(True)
+    pred = model(image)
+    loss = TR.depth_loss(pred, TR.depth_norm(torch.from_numpy(g["depth"]).to(DEV)))
+    loss.backward()
+    torch.cuda.synchronize()
+    params = dict(model.named_parameters())
+    errs = {"pred": rel_l2(pred.detach(), g["pred"]), "dimage": rel_l2(image.grad, g["dimage"]),
+            "loss": abs(float(loss.detach()) - float(g["loss"][0])) / float(g["loss"][0])}
+    for k in MODEL_GRAD_KEYS:
+        errs[k] = rel_l2(params[k].grad, g["grad." + k])
+    _report("full model vs reference golden 64x96", errs)
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, f"{bad}\nall: {errs}"
+
+
 def test_config5_highres_inference_vs_oracle():
     """BASELINE.json configs[4]: 960x1280 inference, batch 16 -> scale 1/4 is 240x320 (245x322 padded, 25 760
     windows per block).  Forward only, no saved tensors; oracle evaluated with torch on the GPU (same oracle code)."""

@@ -70,3 +70,36 @@ def test_loss_matches_reference_golden():
             val.backward()
             assert abs(float(val.detach()) - float(g[f"loss.{tag}"][0])) < 1e-6
             assert rel_l2(pred.grad, g[f"dpred.{tag}"]) < 1e-5
+
+
+def test_full_model_oracle_matches_reference_model():
+    """oracle.model_oracle.OraclePTModel (the CPU baseline / reference arm of bench.py and the checker of the whole-model
+    GPU test) against the UNMODIFIED reference model (src/model_mobileV3_large_newCRFs.py PTModel, executed in the build
+    container by tests/golden/make_golden.py): same name-seeded weights, eval mode, 2 x 3 x 64 x 96 image -- depth map,
+    loss, image gradient and a dozen parameter gradients spread over encoder, bridge, the four stages and the head."""
+    from oracle import model_oracle as MO
+    from tests.helpers import MODEL_GRAD_KEYS, fill_by_name
+    g = load_golden("model_64x96")
+    model = fill_by_name(MO.OraclePTModel()).eval()
+    assert sorted(model.state_dict().keys()) == g["keys"].tolist()          # one checkpoint fits both
+    image = torch.from_numpy(g["image"]).requires_grad_(True)
+    pred = model(image)
+    loss = MO.ssim_l1_loss(pred, MO.depth_norm(torch.from_numpy(g["depth"])))
+    loss.backward()
+    assert rel_l2(pred.detach(), g["pred"]) < 1e-5
+    assert abs(float(loss.detach()) - float(g["loss"][0])) < 1e-6
+    assert rel_l2(image.grad, g["dimage"]) < 1e-4
+    params = dict(model.named_parameters())
+    for k in MODEL_GRAD_KEYS:
+        assert rel_l2(params[k].grad, g["grad." + k]) < 1e-4, k
+
+
+def test_product_model_state_dict_matches_reference_model():
+    """The product model's module tree takes the reference model's checkpoint as-is (keys and shapes)."""
+    from monocular_depth_estimation_b200.model import PTModel
+    from oracle import model_oracle as MO
+    g = load_golden("model_64x96")
+    ours, ref = PTModel().state_dict(), MO.OraclePTModel().state_dict()
+    assert sorted(ours.keys()) == g["keys"].tolist()
+    for k, t in ours.items():
+        assert tuple(t.shape) == tuple(ref[k].shape) and t.dtype == ref[k].dtype, k
