@@ -102,3 +102,28 @@ def train_step(model, optimizer, image, depth, autocast_dtype=torch.bfloat16):
     loss.backward()
     optimizer.step()
     return loss
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") and isinstance(model.module, nn.Module) else model
+
+
+def save_checkpoint(path, model, optimizer, epoch, loss):
+    """The reference loop's checkpoint (src/train.py:143-155): a dict with `epoch`, `model_state_dict`,
+    `optimizer_state_dict`, `loss`.  A DDP-wrapped model is unwrapped first, so the keys are the reference's
+    (`Unet.0...`, `Unet.1...`, never `module.`-prefixed) and the file loads into the reference, a single-GPU run or
+    another DDP run alike.  Under torchrun call it on rank 0 only (parameters are replicated)."""
+    loss_t = loss.detach().cpu() if torch.is_tensor(loss) else torch.tensor(float(loss))
+    torch.save({"epoch": int(epoch), "model_state_dict": _unwrap(model).state_dict(),
+                "optimizer_state_dict": optimizer.state_dict(), "loss": loss_t}, path)
+
+
+def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
+    """Resume as src/train.py:56-67 does: returns (epoch, loss).  Accepts checkpoints written by the reference loop
+    (same format and keys) and ones whose keys carry a DDP `module.` prefix."""
+    ck = torch.load(path, map_location=map_location, weights_only=False)
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["model_state_dict"].items()}
+    _unwrap(model).load_state_dict(sd, strict=True)
+    if optimizer is not None and "optimizer_state_dict" in ck:
+        optimizer.load_state_dict(ck["optimizer_state_dict"])
+    return int(ck.get("epoch", 0)), ck.get("loss")

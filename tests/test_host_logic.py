@@ -85,3 +85,38 @@ def test_glue_host_paths_without_cuda():
                  lambda: CF.crf_layer(torch.randn(1, 49, 64), torch.randn(1, 7, 7, 64), 7, 7, [[None] * 13], 2)):
         with pytest.raises(RuntimeError, match="CUDA"):
             call()
+
+
+def test_checkpoint_format_round_trip(tmp_path):
+    """src/train.py:143-155 / :56-67: {'epoch', 'model_state_dict', 'optimizer_state_dict', 'loss'}; a checkpoint of a
+    wrapped model carries the reference's keys and resumes model and Adam state exactly."""
+    from monocular_depth_estimation_b200 import training as TR
+
+    class Wrapped(torch.nn.Module):          # stands in for DistributedDataParallel (same `.module` convention)
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+    torch.manual_seed(0)
+    a = pkg.NewCRF(input_dim=8, embed_dim=64, v_dim=8, num_heads=2)
+    opt = torch.optim.Adam(a.parameters(), 1e-3)
+    for p in a.parameters():
+        p.grad = torch.randn_like(p)
+    opt.step()
+    path = str(tmp_path / "global_checkpoint.pth")
+    TR.save_checkpoint(path, Wrapped(a), opt, epoch=7, loss=torch.tensor(0.25))
+    raw = torch.load(path, weights_only=False)
+    assert sorted(raw.keys()) == ["epoch", "loss", "model_state_dict", "optimizer_state_dict"]
+    assert sorted(raw["model_state_dict"].keys()) == sorted(a.state_dict().keys())     # no `module.` prefix
+    b = pkg.NewCRF(input_dim=8, embed_dim=64, v_dim=8, num_heads=2)
+    opt_b = torch.optim.Adam(b.parameters(), 1e-3)
+    epoch, loss = TR.load_checkpoint(path, b, opt_b)
+    assert epoch == 7 and float(loss) == 0.25
+    for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(x, y), k
+    sa, sb = opt.state_dict()["state"], opt_b.state_dict()["state"]
+    assert all(torch.equal(sa[i]["exp_avg"], sb[i]["exp_avg"]) for i in sa)
+    # a checkpoint whose keys carry the DDP prefix loads too
+    raw["model_state_dict"] = {"module." + k: v for k, v in raw["model_state_dict"].items()}
+    torch.save(raw, path)
+    TR.load_checkpoint(path, pkg.NewCRF(input_dim=8, embed_dim=64, v_dim=8, num_heads=2))
