@@ -4,7 +4,7 @@
 //
 // STATUS: written after the round-1 GPU budget was spent -- compiles for sm_100a, has NOT run on hardware yet.
 // It is therefore opt-in (CRF_WIDE_HEADS=1, see fill_attn_params) and its GPU tests are isolated in a subprocess
-// (tests/test_zz_gpu_wide_heads.py).  Without the switch head_dim 64 / 128 is rejected exactly as before.
+// (tests/test_zz_gpu_unverified.py).  Without the switch head_dim 64 / 128 is rejected exactly as before.
 //
 // Same mathematics and index maps as crf_attn_async.cu (newcrf_layers.py:121-146, :212-249, :332-350): pad, roll,
 // partition, bias gather, shift mask, softmax, P V, reverse, un-roll and crop never exist in HBM.  A head of width

@@ -38,7 +38,7 @@ def _layer_from_golden(g, C, nH, depth):
 
 
 @pytest.mark.skipif(__import__("os").environ.get("CRF_WIDE_HEADS") != "1",
-                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_wide_heads.py (CRF_WIDE_HEADS=1)")
+                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_unverified.py (CRF_WIDE_HEADS=1)")
 @pytest.mark.parametrize("name", HEAD_CASES)
 def test_head_width_golden(name):
     """The reference's own outputs / gradients for one 64-wide head and for four 16-wide heads."""
@@ -208,7 +208,7 @@ def test_head_dim_16_block_vs_oracle(H, W, C, nH, shift):
 
 
 @pytest.mark.skipif(__import__("os").environ.get("CRF_WIDE_HEADS") != "1",
-                    reason="head_dim 64/128 is opt-in: CRF_WIDE_HEADS=1 (tests/test_zz_gpu_wide_heads.py)")
+                    reason="head_dim 64/128 is opt-in: CRF_WIDE_HEADS=1 (tests/test_zz_gpu_unverified.py)")
 @pytest.mark.parametrize("H,W,C,nH,shift", [(9, 10, 64, 1, 3), (30, 40, 128, 2, 0), (15, 20, 256, 4, 3), (15, 20, 256, 2, 0),
                                             (30, 40, 512, 8, 3), (16, 23, 512, 4, 3)])
 def test_wide_head_block_vs_oracle(H, W, C, nH, shift):
@@ -283,7 +283,7 @@ def test_full_model_dropin_matches_oracle_model():
 
 
 @pytest.mark.skipif(__import__("os").environ.get("CRF_WIDE_HEADS") != "1",
-                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_wide_heads.py (CRF_WIDE_HEADS=1)")
+                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_unverified.py (CRF_WIDE_HEADS=1)")
 def test_full_model_matches_reference_model_golden():
     """The product model against the UNMODIFIED reference model's own numbers (tests/golden/model_64x96.npz: name-seeded
     weights, eval mode): depth map, loss, image gradient, parameter gradients across encoder, bridge, stages and head."""

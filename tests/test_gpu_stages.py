@@ -347,7 +347,7 @@ def test_attn_fwd(B, H, W, C, nH, shift):
     _check(lse[:, :, :49], ref_lse, 1e-4, "attn_fwd.lse")
 
 
-# head_dim 64 / 128 (crf_attn_wide.cu): opt-in until it has run on hardware -- tests/test_zz_gpu_wide_heads.py runs these
+# head_dim 64 / 128 (crf_attn_wide.cu): opt-in until it has run on hardware -- tests/test_zz_gpu_unverified.py runs these
 # in a subprocess with CRF_WIDE_HEADS=1; a plain `pytest -m gpu` skips them.
 wide_only = pytest.mark.skipif(os.environ.get("CRF_WIDE_HEADS") != "1", reason="head_dim 64/128 is opt-in: CRF_WIDE_HEADS=1")
 WIDE_CASES = [(1, 7, 7, 64, 1, 0), (2, 9, 10, 64, 1, 3), (1, 14, 14, 128, 2, 0), (1, 15, 20, 128, 1, 3),
