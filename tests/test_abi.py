@@ -77,3 +77,61 @@ def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
+
+
+def _sizes(lib, d):
+    s, f, b = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    rc = lib.crf_block_sizes(ctypes.byref(d), ctypes.byref(s), ctypes.byref(f), ctypes.byref(b))
+    return rc, s.value, f.value, b.value
+
+
+def test_buffer_sizes_host_side():
+    """crf_block_sizes / crf_layer_sizes are pure host arithmetic: check them without a GPU -- 256-byte granularity,
+    inference < training, growth with the problem, and the figure DESIGN.md quotes for the 1/4 scale of config 2."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("extension not built")
+    from monocular_depth_estimation_b200 import ops
+    lib = _lib.lib()
+    d = ops.make_desc(8, 120, 160, 128, 4, 3, device=0)
+    rc, saved, _, ws = _sizes(lib, d)
+    assert rc == 0 and saved % 256 == 0 and ws % 256 == 0
+    T, C = 8 * 120 * 160, 128
+    # xn1, qk(2C), vb, attn_o, xn2 bf16 + x1 fp32 + pre, act (4C bf16 each) + bf16 weights + stats / lse
+    floor = T * C * (2 + 4 + 2 + 2 + 2 + 4 + 8 + 8)
+    assert floor <= saved <= int(floor * 1.1) + (1 << 20), (saved, floor)
+    assert 0.55e9 < saved < 0.80e9            # "about 0.75 GB per block" (DESIGN.md section 2)
+    d_inf = ops.make_desc(8, 120, 160, 128, 4, 3, device=0, training=0)
+    assert _sizes(lib, d_inf)[1] < saved       # no pre-activation kept for inference
+    small = ops.make_desc(2, 60, 80, 128, 4, 3, device=0)
+    assert _sizes(lib, small)[1] < saved and _sizes(lib, small)[3] < ws
+    # layer level: two blocks + shared v + intermediate outputs; more than two stand-alone blocks' saved areas minus v
+    sb, wb = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.crf_layer_sizes(ctypes.byref(d), 2, 1, ctypes.byref(sb), ctypes.byref(wb)) == 0
+    assert sb.value > 2 * (saved - T * C * 2 - 4096) and wb.value >= ws
+    assert lib.crf_layer_sizes(ctypes.byref(d), 0, 0, ctypes.byref(sb), ctypes.byref(wb)) != 0
+    assert b"depth" in lib.crf_last_error()
+
+
+def test_head_width_validation_and_opt_in_switch():
+    """head_dim 16 / 32 are accepted, anything else is rejected with the reference-style message; 64 / 128 only with
+    CRF_WIDE_HEADS=1 (read once per process, hence the subprocess)."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("extension not built")
+    import subprocess
+    import sys
+    from monocular_depth_estimation_b200 import ops
+    lib = _lib.lib()
+    for C, nH, ok in [(128, 4, True), (128, 8, True), (128, 2, False), (128, 1, False), (64, 8, False), (128, 3, False)]:
+        rc = _sizes(lib, ops.make_desc(1, 7, 7, C, nH, 0, device=0))[0]
+        assert (rc == 0) == ok, (C, nH)
+        if not ok:
+            assert b"head_dim must be 16 or 32" in lib.crf_last_error()
+    code = ("import ctypes, sys; sys.path.insert(0, %r)\n"
+            "from monocular_depth_estimation_b200 import _lib, ops\n"
+            "lib = _lib.lib(); s = ctypes.c_size_t()\n"
+            "r = [lib.crf_block_sizes(ctypes.byref(ops.make_desc(1, 7, 7, C, nH, 0, device=0)), ctypes.byref(s), None, None)"
+            " for C, nH in [(128, 2), (128, 1), (64, 1), (64, 8)]]\n"
+            "print(r)\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CRF_WIDE_HEADS="1"), check=True,
+                         capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    assert out == "[0, 0, 0, 1]", out   # 64, 128, 64 accepted; head_dim 8 still rejected
