@@ -6,7 +6,10 @@ Group B -- new KERNELS: head_dim 64 / 128 (csrc/crf_attn_wide.cu, BASELINE.json 
 but are opt-in (CRF_WIDE_HEADS=1) until they have run: stage-level forward / backward, block level against the oracle,
 the reference's golden vectors for one 64-wide head.
 
-Each group runs in its own SUBPROCESS with CRF_WIDE_HEADS=1 and a hard time limit, so that a device-side fault of an
+Group C -- a candidate KERNEL for an existing stage: the multi-row LayerNorm forward (CRF_LN_ROWS=4, csrc/crf_misc.cu
+ln_fwd_multirow_kernel; bit-identical arithmetic, more bytes in flight per warp), run through the existing LayerNorm cases.
+
+Each group runs in its own SUBPROCESS with its opt-in switch set and a hard time limit, so that a device-side fault of an
 unverified kernel cannot poison the CUDA context of the verified suite (this file also sorts last), and is reported as
 xfail / xpass (non-strict) instead of failing the run.  The tails of the pytest output are kept under gpurun_out/.
 Once a group is green on a B200, drop the switch and fold its cases into the plain suite.
@@ -20,18 +23,24 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-GROUPS = {
-    "new_checks": "hd16 or test_full_model_matches_reference_model_golden",
-    "wide_heads": "test_attn_fwd_wide or test_attn_bwd_wide or test_wide_head_block_vs_oracle or hd64",
+GROUPS = {   # name: (pytest -k expression, extra environment)
+    "new_checks": ("hd16 or test_full_model_matches_reference_model_golden", {"CRF_WIDE_HEADS": "1"}),
+    "wide_heads": ("test_attn_fwd_wide or test_attn_bwd_wide or test_wide_head_block_vs_oracle or hd64",
+                   {"CRF_WIDE_HEADS": "1"}),
+    # Group C -- candidate kernel: LayerNorm forward with 4 rows in flight per warp (CRF_LN_ROWS=4), through the
+    # existing LayerNorm / conversion parity cases and one whole block
+    "ln_multirow": ("test_ln_fwd or test_layer_norm_standalone or test_colsum_cast_convert or test_config1_block",
+                    {"CRF_LN_ROWS": "4"}),
 }
 
 
 @pytest.mark.xfail(strict=False, reason="cases added after the round-1 GPU budget was spent: not yet run on hardware")
 @pytest.mark.parametrize("group", list(GROUPS))
 def test_unverified_cases_isolated(group):
-    env = dict(os.environ, CRF_WIDE_HEADS="1")
+    kexpr, extra = GROUPS[group]
+    env = dict(os.environ, **extra)
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_stages.py", "tests/test_gpu_block.py", "-q", "-m", "gpu",
-           "-k", GROUPS[group], "-p", "no:cacheprovider"]
+           "-k", kexpr, "-p", "no:cacheprovider"]
     try:
         r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
         rc, tail = r.returncode, (r.stdout or "")[-4000:] + (r.stderr or "")[-1500:]
