@@ -60,6 +60,8 @@ def parse_args():
                     help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--cudnn-benchmark", type=int, default=0,
                     help="1: torch.backends.cudnn.benchmark (cuDNN autotunes the stock convolutions during warm-up)")
+    ap.add_argument("--lib-adam", action="store_true",
+                    help="use the library's one-launch Adam step (crf_adam_step) instead of torch's fused Adam; opt-in")
     ap.add_argument("--ddp-grad-bf16", action="store_true",
                     help="N>1: exchange the gradient buckets in bf16 (90 MB instead of 180 MB per step); off by default")
     ap.add_argument("--memory-format", default="channels_last", choices=["contiguous", "channels_last"],
@@ -205,7 +207,11 @@ def run_ours(args):
     else:
         net = wrap_ddp(model, device, world, grad_dtype=grad_dtype)
     # same update as train.py:41 in one fused kernel; capturable so the step can live in a CUDA graph
-    opt = torch.optim.Adam(model.parameters(), 1e-4, fused=True, capturable=use_graph)
+    if args.lib_adam:   # opt-in: the library's one-launch Adam (training.LibAdam); not yet verified on hardware
+        from monocular_depth_estimation_b200.training import LibAdam
+        opt = LibAdam([p for p in model.parameters() if p.requires_grad], 1e-4)
+    else:
+        opt = torch.optim.Adam(model.parameters(), 1e-4, fused=True, capturable=use_graph)
 
     image_h = torch.rand(B, 3, H, W).contiguous(memory_format=mf).pin_memory()
     depth_h = torch.rand(B, 1, H, W).pin_memory()
@@ -473,6 +479,7 @@ def run_ours(args):
                    "gradient_exchange": "none (1 GPU)" if world == 1 else
                    ("NCCL all-reduce, bf16 buckets" if args.ddp_grad_bf16 else "NCCL all-reduce, fp32 buckets"),
                    "cuda_graph": graph is not None,
+                   "optimizer": "library Adam (crf_adam_step)" if args.lib_adam else "torch.optim.Adam(fused=True)",
                    "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush",
                    "precision": "bf16 tensor-core operands + bf16 intermediates, fp32 accumulate/softmax/LN/residual; "
                                 "encoder and convs under torch bf16 autocast"},

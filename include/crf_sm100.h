@@ -233,6 +233,23 @@ int crf_depth_loss_bwd(const void* pred, int pred_dtype, const float* target, co
  * B, H, W, C always describe the (B, H, W, C) side; C % 4 == 0. */
 int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, int inverse, int device,
                            void* stream);
+/* One Adam step over many fp32 tensors (replaces torch.optim.Adam.step of the reference loop,
+ * /root/reference/src/train.py:41,108; no amsgrad; weight_decay is torch's L2 form, 0 in the reference).
+ *   tensors  HOST array of n_tensors records (device pointers inside); passed to the kernels as launch arguments,
+ *            80 tensors per launch, so nothing has to stay alive after the call
+ *   chunk_elems  elements one CTA updates (multiple of 4, >= 1024; 16384 is a good value)
+ *   step     DEVICE float: number of steps taken so far; the update uses step + 1 and the call then increments it
+ *            (so a CUDA graph that captured the call keeps counting on replay)
+ * EXPERIMENTAL in ABI version 1: the element update is host-verified against torch, the kernel has not run on hardware. */
+typedef struct crf_adam_tensor {
+  float* p;        /* parameter, updated in place */
+  const float* g;  /* gradient */
+  float* m;        /* exp_avg, updated in place */
+  float* v;        /* exp_avg_sq, updated in place */
+  int64_t n;       /* elements */
+} crf_adam_tensor;
+int crf_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float* step, int device, void* stream);
 /* out[n] += sum_t g[t, n], g bf16 (T, N) contiguous, N % 4 == 0 */
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
 /* f32 -> bf16 contiguous */

@@ -28,8 +28,12 @@ EXPORTED_SYMBOLS = (
     "crf_layer_sizes", "crf_layer_fwd", "crf_layer_bwd",
     "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_gemm_workspace_bytes", "crf_ln_fwd", "crf_ln_bwd",
     "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd", "crf_pixel_shuffle_nhwc",
-    "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd",
+    "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd", "crf_adam_step",
 )
+
+
+class AdamTensor(C.Structure):          # include/crf_sm100.h: crf_adam_tensor
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
 
 
 class BlockDesc(C.Structure):
@@ -110,6 +114,7 @@ def _declare(lib):
     lib.crf_pixel_shuffle_nhwc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_colsum_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.crf_cast_bf16.argtypes = [vp, vp, i64, i32, vp]
+    lib.crf_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, f32, f32, f32, f32, f32, vp, i32, vp]
     lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp]
     lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:

@@ -127,3 +127,87 @@ def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
     if optimizer is not None and "optimizer_state_dict" in ck:
         optimizer.load_state_dict(ck["optimizer_state_dict"])
     return int(ck.get("epoch", 0)), ck.get("loss")
+
+
+class LibAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr) of the reference loop (src/train.py:41, :108) as the library's multi-tensor step
+    (crf_adam_step: 80 tensors per launch, pointers passed as launch arguments) instead of torch's multi-tensor launches;
+    same update, same state layout (`exp_avg`, `exp_avg_sq`, `step` per parameter), so optimizer_state_dict entries of
+    the reference's checkpoints load.  The step counter lives on the device, hence a CUDA graph that captured the step
+    keeps counting on replay.  CUDA fp32 parameters only.
+
+    EXPERIMENTAL: the element update is verified on the host against torch.optim.Adam (tests/test_adam_host.py); the
+    kernel was written after the round-1 GPU budget was spent and has not run on hardware -- opt-in
+    (`bench.py --lib-adam`); the default remains torch's fused Adam."""
+
+    CHUNK = 16384   # elements per CTA (64 KB of each of p, g, m, v)
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("LibAdam: invalid hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @staticmethod
+    def chunk_counts(numels, chunk):
+        """CTAs per tensor: crf_adam_step gives CTA c of a tensor the elements [c * chunk, min(n, (c + 1) * chunk))."""
+        return [(int(n) + chunk - 1) // chunk for n in numels]
+
+    def _init_group(self, group):
+        ps = [p for p in group["params"] if p.requires_grad]
+        for p in ps:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise RuntimeError("LibAdam: parameters must be contiguous CUDA fp32 tensors (there is no CPU path)")
+        missing = [p for p in ps if "exp_avg" not in self.state[p]]
+        if missing:
+            dev = missing[0].device
+            sizes = [(p.numel() + 3) // 4 * 4 for p in missing]           # keep every view 16-byte aligned
+            flat_m = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            flat_v = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            if group.get("_step") is None:
+                group["_step"] = torch.zeros((), dtype=torch.float32, device=dev)
+            o = 0
+            for p, n in zip(missing, sizes):
+                self.state[p]["step"] = group["_step"]
+                self.state[p]["exp_avg"] = flat_m[o:o + p.numel()].view_as(p)
+                self.state[p]["exp_avg_sq"] = flat_v[o:o + p.numel()].view_as(p)
+                o += n
+        return ps
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:   # one device counter per group again (torch keeps one per parameter)
+            have = [p for p in group["params"] if p in self.state and "step" in self.state[p]]
+            if have:
+                step = torch.as_tensor(float(self.state[have[0]]["step"]), dtype=torch.float32)
+                group["_step"] = step.to(have[0].device).reshape(())
+                for p in have:
+                    self.state[p]["step"] = group["_step"]
+                    for k in ("exp_avg", "exp_avg_sq"):
+                        self.state[p][k] = self.state[p][k].to(device=p.device, dtype=torch.float32).contiguous()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        import ctypes as C
+        from . import _lib as L
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps = [p for p in self._init_group(group) if p.grad is not None]
+            if not ps:
+                continue
+            dev = ps[0].device
+            recs = (L.AdamTensor * len(ps))()
+            for r, p in zip(recs, ps):
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous() or g.device != dev:
+                    raise RuntimeError("LibAdam: gradients must be contiguous fp32 tensors on the parameters' device")
+                st = self.state[p]
+                r.p, r.g, r.m, r.v, r.n = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+            b1, b2 = group["betas"]
+            L.check(L.lib().crf_adam_step(recs, len(ps), self.CHUNK, float(group["lr"]), float(b1), float(b2),
+                                          float(group["eps"]), float(group["weight_decay"]), group["_step"].data_ptr(),
+                                          dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                    "crf_adam_step")
+        return loss

@@ -60,7 +60,8 @@ def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     structs = {"crf_block_desc": _lib.BlockDesc, "crf_block_params": _lib.BlockParams,
-               "crf_block_grads": _lib.BlockGrads, "crf_layer_args": _lib.LayerArgs, "crf_gemm_args": _lib.GemmArgs}
+               "crf_block_grads": _lib.BlockGrads, "crf_layer_args": _lib.LayerArgs, "crf_gemm_args": _lib.GemmArgs,
+               "crf_adam_tensor": _lib.AdamTensor}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "crf_sm100.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

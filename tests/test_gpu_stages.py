@@ -422,3 +422,42 @@ def test_attn_bwd(B, H, W, C, nH, shift):
     if bs_r.grad[C:].abs().max() > 0:
         _check(d_bias[C:], bs_r.grad[C:], 1.5e-2, "attn_bwd.d_bias_k")
     assert d_bias[:C].abs().max() == 0
+
+
+@pytest.mark.skipif(os.environ.get("CRF_TEST_LIB_ADAM") != "1",
+                    reason="added after the GPU budget was spent: runs from tests/test_zz_gpu_unverified.py")
+def test_lib_adam_matches_torch_adam():
+    """training.LibAdam (crf_adam_step: one launch for all tensors, device-side step counter) against torch.optim.Adam
+    on identical parameters / gradients over several steps, including odd sizes, an unaligned view and a state_dict
+    round trip into torch's optimizer."""
+    from monocular_depth_estimation_b200.training import LibAdam
+    torch.manual_seed(0)
+    shapes = [(1,), (3,), (169, 4), (128, 128), (512, 128), (16385,), (1024, 1031), (7, 5, 3)]
+    base = torch.randn(40, device=DEV)
+    ours = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    ours.append(torch.nn.Parameter(base[1:34]))                    # 4-byte-aligned view: scalar path
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    oa = LibAdam(ours, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    ob = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(6):
+        for a, b in zip(ours, ref):
+            g = torch.randn_like(a) * (10.0 ** (step - 3))
+            a.grad, b.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ours, ref):
+        assert (a - b).abs().max() <= 3e-7 * max(1.0, float(b.abs().max())), a.shape
+        _check(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"], 1e-5, "exp_avg")
+        _check(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], 1e-5, "exp_avg_sq")
+    assert float(oa.state[ours[0]]["step"]) == 6.0
+    # torch's optimizer accepts our state (same layout), and ours accepts torch's
+    ob2 = torch.optim.Adam(ref, lr=1e-3)
+    ob2.load_state_dict(oa.state_dict())
+    oa2 = LibAdam(ours, lr=1e-3)
+    oa2.load_state_dict(ob.state_dict())
+    for a in ours:
+        a.grad = torch.ones_like(a)
+    oa2.step()
+    torch.cuda.synchronize()
+    assert float(oa2.state[ours[0]]["step"]) == 7.0
