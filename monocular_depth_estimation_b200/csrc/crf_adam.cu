@@ -44,14 +44,18 @@ adam_multi_kernel(const __grid_constant__ AdamBatch B, int chunk_elems, float lr
   float* m = B.m[ti] + lo;
   float* v = B.v[ti] + lo;
   const int n = static_cast<int>(hi - lo);
-  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  // p, m, v vectorised when 16-byte aligned (separately allocated parameters and the optimizer's padded state views
+  // always are); the gradient may be an arbitrarily aligned view of a DDP bucket: four scalar loads then
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const bool gvec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
   int done = 0;
   if (vec) {
     const int n4 = n >> 2;
     for (int i = threadIdx.x; i < n4; i += kAdamThreads) {
       float4 pp = reinterpret_cast<float4*>(p)[i];
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+      float4 gg;
+      if (gvec) gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+      else gg = make_float4(__ldg(g + 4 * i), __ldg(g + 4 * i + 1), __ldg(g + 4 * i + 2), __ldg(g + 4 * i + 3));
       float4 mm = reinterpret_cast<float4*>(m)[i];
       float4 vv = reinterpret_cast<float4*>(v)[i];
       adam_update(c, pp.x, gg.x, mm.x, vv.x);
