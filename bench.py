@@ -60,6 +60,9 @@ def parse_args():
                     help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--cudnn-benchmark", type=int, default=0,
                     help="1: torch.backends.cudnn.benchmark (cuDNN autotunes the stock convolutions during warm-up)")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="N=1: also time the oracle port of the reference's eager PyTorch path on this GPU (reported as "
+                         "gpu_eager_baseline; SURVEY.md 8d); off by default")
     ap.add_argument("--lib-adam", action="store_true",
                     help="use the library's one-launch Adam step (crf_adam_step) instead of torch's fused Adam; opt-in")
     ap.add_argument("--ddp-grad-bf16", action="store_true",
@@ -463,6 +466,33 @@ def run_ours(args):
                                     "tensor_tflops": k["flops"] / us / 1e6}
             crf_blocks.append(ent)
 
+    gpu_eager = None
+    if world == 1 and args.gpu_eager_baseline:
+        # The reference's GPU path is eager PyTorch; the Python reference cannot travel to the GPU box, so this times its
+        # restatement with the same torch ops (oracle/model_oracle.py) on THIS GPU, same config, bf16 autocast, fused Adam,
+        # stock PyTorch kernels only -- a reported baseline next to cpu_baseline, never part of `value`.
+        from oracle import model_oracle as MO
+        torch.manual_seed(0)
+        ref_model = MO.OraclePTModel().to(device).train().to(memory_format=mf)
+        ref_opt = torch.optim.Adam(ref_model.parameters(), 1e-4, fused=True)
+
+        def ref_step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                pred = ref_model(image_d)
+            loss_r = MO.ssim_l1_loss(pred.float(), MO.depth_norm(depth_d))
+            ref_opt.zero_grad(set_to_none=True)
+            loss_r.backward()
+            ref_opt.step()
+
+        for _ in range(3):
+            ref_step()
+        k = max(3, min(args.steps, 5))
+        ms_ref = timed(ref_step, k)
+        gpu_eager = {"value": B * k / (ms_ref * 1e-3), "unit": UNIT, "ms_per_step": ms_ref / k,
+                     "kind": "oracle port of the reference's PyTorch path, eager, on this GPU (stock PyTorch kernels, "
+                             "bf16 autocast, channels-last, fused Adam; no CUDA graph)"}
+        del ref_model, ref_opt
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_run(args.ref_batch, H, W, steps=2, warmup=1)
@@ -498,6 +528,8 @@ def run_ours(args):
         line["crf_blocks"] = crf_blocks
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if gpu_eager is not None:
+        line["gpu_eager_baseline"] = gpu_eager
     emit(line)
     finish()
 
