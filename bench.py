@@ -60,6 +60,9 @@ def parse_args():
                     help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--cudnn-benchmark", type=int, default=0,
                     help="1: torch.backends.cudnn.benchmark (cuDNN autotunes the stock convolutions during warm-up)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="BASELINE configs[3]: fixed global batch (64) sharded over the ranks, i.e. strong scaling; "
+                         "0 (default): --batch images per GPU, weak scaling")
     ap.add_argument("--gpu-eager-baseline", action="store_true",
                     help="N=1: also time the oracle port of the reference's eager PyTorch path on this GPU (reported as "
                          "gpu_eager_baseline; SURVEY.md 8d); off by default")
@@ -195,6 +198,10 @@ def run_ours(args):
     torch.manual_seed(1234 + rank)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     B, H, W = args.batch, args.height, args.width
+    if args.global_batch:   # BASELINE.json configs[3]: a fixed global batch sharded over the ranks (strong scaling)
+        if args.global_batch % world:
+            raise SystemExit(f"bench.py: --global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world
 
     model = PTModel().to(device).train()
     mf = torch.channels_last if args.memory_format == "channels_last" else torch.contiguous_format
@@ -501,7 +508,8 @@ def run_ours(args):
     imgs = B * world * args.steps
     line = {
         "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"MobileNetV3-large + NeWCRFs decoder train step (fwd + SSIM/L1 loss + bwd + Adam), "
                                f"{H}x{W}, batch {B} per GPU (BASELINE.json configs[1])",
