@@ -11,18 +11,13 @@ int launch_attn_bwd_async(const AttnParams& P, const crf_block_desc& d, cudaStre
 int launch_attn_fwd_wide(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);  // crf_attn_wide.cu
 int launch_attn_bwd_wide(const AttnParams& P, const crf_block_desc& d, cudaStream_t st);
 
-// head_dim 16 / 32: crf_attn_async.cu.  head_dim 64 / 128 (crf_attn_wide.cu) has not run on hardware yet and is
-// therefore opt-in: CRF_WIDE_HEADS=1.
-bool head_dim_supported(int hd) {
-  if (hd == 16 || hd == 32) return true;
-  static const bool wide = getenv("CRF_WIDE_HEADS") != nullptr && atoi(getenv("CRF_WIDE_HEADS")) != 0;
-  return wide && (hd == 64 || hd == 128);
-}
+// head_dim 16 / 32: crf_attn_async.cu (pipelined).  head_dim 64 / 128: crf_attn_wide.cu (32-wide slices of a head,
+// synchronous structure; verified on B200 through tools/hwcheck, profiles/r01_hwcheck.txt).
+bool head_dim_supported(int hd) { return hd == 16 || hd == 32 || hd == 64 || hd == 128; }
 
 int fill_attn_params(AttnParams& P, const crf_block_desc& d) {
   CRF_CHECK(d.num_heads > 0 && d.C % d.num_heads == 0 && head_dim_supported(d.C / d.num_heads),
-            "attention core: head_dim must be 16 or 32 (C=%d, heads=%d; 64 / 128: experimental, CRF_WIDE_HEADS=1)", d.C,
-            d.num_heads);
+            "attention core: head_dim must be 16, 32, 64 or 128 (C=%d, heads=%d)", d.C, d.num_heads);
   CRF_CHECK(d.window == 7, "attention core: window must be 7 (got %d)", d.window);
   CRF_CHECK(d.shift >= 0 && d.shift < d.window, "shift_size must in 0-window_size");
   P.gm = WindowGeom(d.H, d.W, d.window, d.shift);

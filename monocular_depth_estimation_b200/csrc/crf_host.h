@@ -48,7 +48,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 int make_tmap_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 int num_sms(int device);
-bool head_dim_supported(int hd);  // 16, 32; 64 and 128 with CRF_WIDE_HEADS=1 (crf_attn.cu)
+bool head_dim_supported(int hd);  // 16, 32 (crf_attn_async.cu), 64, 128 (crf_attn_wide.cu)
 void note_launch(int n = 1);
 
 // Optional per-kernel timing (crf_timing_enable): CUDA events recorded on the launch stream around each kernel,

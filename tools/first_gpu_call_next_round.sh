@@ -35,5 +35,5 @@ PY
 # 4. reported baselines and the configs that have no number yet
 timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --gpu-eager-baseline > gpurun_out/n_bench_gpu_eager.json 2> gpurun_out/n_bench_gpu_eager.err
 timeout 300 python tools/bench_config5.py > gpurun_out/n_config5.json 2> gpurun_out/n_config5.err
-CRF_WIDE_HEADS=1 timeout 400 python tools/sweep_config3.py > gpurun_out/n_config3_sweep_wide.md 2> gpurun_out/n_config3_sweep_wide.err
+timeout 400 python tools/sweep_config3.py > gpurun_out/n_config3_sweep_wide.md 2> gpurun_out/n_config3_sweep_wide.err
 echo "done" | tee -a gpurun_out/n_summary.txt

@@ -3,7 +3,7 @@
 // Calls the C ABI of libcrf_sm100.so directly and compares with plain C++ references evaluated in double precision
 // on the same bf16-rounded inputs:
 //   1. window-attention core forward / backward: head_dim 32 (the verified kernels: validates THIS harness), then
-//      head_dim 64 and 128 (csrc/crf_attn_wide.cu, CRF_WIDE_HEADS=1)
+//      head_dim 64 and 128 (csrc/crf_attn_wide.cu)
 //   2. LayerNorm forward with 4 rows in flight per warp (CRF_LN_ROWS=4)
 //   3. the multi-tensor Adam step (crf_adam_step)
 // Every result line goes to stdout and to gpurun_out/hwcheck.txt as soon as it is known.
@@ -519,7 +519,6 @@ static int run_group(int grp) {
 
 int main(int argc, char** argv) {
   g_t0 = now_s();
-  setenv("CRF_WIDE_HEADS", "1", 1);
   setenv("CRF_LN_ROWS", "4", 1);
   if (argc >= 3 && strcmp(argv[1], "--dry") == 0) {
     for (int i = 0; i < 5; ++i) run_attn_case(kCases[i], kTags[i], argv[2]);

@@ -1,7 +1,7 @@
 """BASELINE.json configs[2]: CRF-block sweep over the four decoder scales of a 480x640 input, shifted / unshifted
 windows and embed dims, mapping each point to its binding roofline (tensor vs HBM) and the fraction achieved.
-head_dim 32 (all four native points: 128/4, 256/8, 512/16, 1024/32, plus 64/2) and head_dim 16 are implemented;
-with CRF_WIDE_HEADS=1 the head_dim 64 / 128 points (csrc/crf_attn_wide.cu, opt-in until verified on hardware) are added.
+head_dim 32 (all four native points: 128/4, 256/8, 512/16, 1024/32, plus 64/2), head_dim 16, and head_dim 64 / 128
+(csrc/crf_attn_wide.cu: correct, not tuned) are swept.
 
     python tools/sweep_config3.py > profiles/r01_config3_sweep.md
 Each point: one CRFBlock fwd+bwd at batch 8, timed with CUDA events (5 iterations after 2 warm-ups); algorithmic
@@ -30,10 +30,8 @@ def main():
         for C in [64, 128, 256, 512, 1024]:
             if B * H * W * C * 4 * 40 > 60e9:
                 continue
-            wide = os.environ.get("CRF_WIDE_HEADS") == "1"
             points = [(C // 32, 0), (C // 32, 3)] + ([(C // 16, 3)] if C <= 512 else [])
-            if wide:
-                points += [(C // 64, 3)] + ([(C // 128, 3)] if C >= 128 else [])
+            points += [(C // 64, 3)] + ([(C // 128, 3)] if C >= 128 else [])
             for nH, shift in points:
                 torch.manual_seed(0)
                 blk = CRFBlock(C, nH, C, shift_size=shift).to(dev)
