@@ -7,8 +7,7 @@
 //   2. LayerNorm forward with 4 rows in flight per warp (CRF_LN_ROWS=4)
 //   3. the multi-tensor Adam step (crf_adam_step)
 // Every result line goes to stdout and to gpurun_out/hwcheck.txt as soon as it is known.
-//   nvcc -O2 -std=c++17 -I include -I monocular_depth_estimation_b200/csrc tools/hwcheck.cu -o tools/hwcheck \
-//        -L monocular_depth_estimation_b200/csrc -lcrf_sm100 -Xlinker -rpath -Xlinker '$ORIGIN/../monocular_depth_estimation_b200/csrc'
+//   make -C monocular_depth_estimation_b200/csrc hwcheck
 //   tools/hwcheck            (on a B200)          tools/hwcheck --dry DIR   (no GPU: dumps inputs + references to DIR)
 #include <cuda_runtime.h>
 #include <math.h>
