@@ -217,7 +217,7 @@ def run_ours(args):
     else:
         net = wrap_ddp(model, device, world, grad_dtype=grad_dtype)
     # same update as train.py:41 in one fused kernel; capturable so the step can live in a CUDA graph
-    if args.lib_adam:   # opt-in: the library's one-launch Adam (training.LibAdam); not yet verified on hardware
+    if args.lib_adam:   # opt-in: the library's Adam (training.LibAdam): correct on hardware (profiles/r01_hwcheck.txt), speed unmeasured
         from monocular_depth_estimation_b200.training import LibAdam
         opt = LibAdam([p for p in model.parameters() if p.requires_grad], 1e-4)
     else:

@@ -240,7 +240,7 @@ int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, 
  *   chunk_elems  elements one CTA updates (multiple of 4, >= 1024; 16384 is a good value)
  *   step     DEVICE float: number of steps taken so far; the update uses step + 1 and the call then increments it
  *            (so a CUDA graph that captured the call keeps counting on replay)
- * EXPERIMENTAL in ABI version 1: the element update is host-verified against torch, the kernel has not run on hardware. */
+ * Verified against the host update on a B200 (profiles/r01_hwcheck.txt); not yet used by default (bench.py --lib-adam). */
 typedef struct crf_adam_tensor {
   float* p;        /* parameter, updated in place */
   const float* g;  /* gradient */

@@ -6,8 +6,9 @@
 // accesses (scalar when a view is not 16-byte aligned).  The step counter lives in device memory (one float,
 // incremented by a last tiny launch), so replays of a captured step keep counting.
 //
-// STATUS: written after the round-1 GPU budget was spent; the element update (crf_adam_math.h) is verified on the host
-// against torch.optim.Adam, the kernel itself has not run on hardware.  Opt-in (training.LibAdam / bench.py --lib-adam).
+// STATUS: the element update (crf_adam_math.h) is verified on the host against torch.optim.Adam; the kernel on a B200
+// against the same update through tools/hwcheck (profiles/r01_hwcheck.txt: bit-identical).  Speed and graph capture are
+// unmeasured: opt-in (training.LibAdam / bench.py --lib-adam).
 #include "crf_adam_math.h"
 #include "crf_host.h"
 

@@ -151,7 +151,7 @@ ln_fwd_rows_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img,
 // Same row kernel with R rows per warp iteration: all R rows' loads are issued before the first reduction, so a warp
 // keeps R x C x sizeof(TIn) bytes in flight instead of one row's (the one-row form is latency-bound for narrow rows:
 // 512 B per warp at C = 128 fp32, 0.53 of the HBM peak measured).  Per-row arithmetic and its order are exactly those
-// of ln_fwd_rows_kernel, so the results are bit-identical.  CANDIDATE, not yet run on hardware: selected only with
+// of ln_fwd_rows_kernel.  CANDIDATE: correct on a B200 (profiles/r01_hwcheck.txt), speed unmeasured: selected only with
 // CRF_LN_ROWS=2|4 (launch_ln_fwd_t / launch_layernorm_fwd); the default path is ln_fwd_rows_kernel.
 template <typename TIn, int NCH, bool DO_LN, typename TOut, int R>
 __global__ void __launch_bounds__(256)

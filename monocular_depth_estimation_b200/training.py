@@ -136,9 +136,10 @@ class LibAdam(torch.optim.Optimizer):
     the reference's checkpoints load.  The step counter lives on the device, hence a CUDA graph that captured the step
     keeps counting on replay.  CUDA fp32 parameters only.
 
-    EXPERIMENTAL: the element update is verified on the host against torch.optim.Adam (tests/test_adam_host.py); the
-    kernel was written after the round-1 GPU budget was spent and has not run on hardware -- opt-in
-    (`bench.py --lib-adam`); the default remains torch's fused Adam."""
+    Status: the element update is verified on the host against torch.optim.Adam (tests/test_adam_host.py) and the kernel
+    on a B200 against the same update (tools/hwcheck, profiles/r01_hwcheck.txt: bit-identical, incl. an unaligned
+    gradient view and the device step counter); its speed and its capture in a CUDA graph have not been measured yet --
+    opt-in (`bench.py --lib-adam`); the default remains torch's fused Adam."""
 
     CHUNK = 16384   # elements per CTA (64 KB of each of p, g, m, v)
 
