@@ -6,9 +6,15 @@ set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 
+# 0. seconds, no Python: correctness of the opt-in kernels through the C ABI, then CUDA-event timings at config-2 sizes
+#    (LayerNorm rows 1 / 2 / 4, Adam over 45 M parameters, attention at head_dim 32 / 64 / 128)
+make -C monocular_depth_estimation_b200/csrc hwcheck > /dev/null 2>&1
+timeout 60 ./tools/hwcheck > gpurun_out/n_hwcheck.log 2>&1; echo "hwcheck rc=$? ($(grep -c PASS gpurun_out/n_hwcheck.log) PASS, $(grep -c FAIL gpurun_out/n_hwcheck.log) FAIL)" | tee gpurun_out/n_summary.txt
+timeout 120 ./tools/hwcheck --bench > gpurun_out/n_hwcheck_bench.log 2>&1; grep bench gpurun_out/n_hwcheck_bench.log | tee -a gpurun_out/n_summary.txt
+
 # 1. the verified suite must still be green on the rebuilt library (new translation units were added to the .so)
 timeout 900 python -m pytest tests -x -q -m gpu --deselect tests/test_zz_gpu_unverified.py > gpurun_out/n_tests_verified.log 2>&1
-echo "verified suite rc=$?" | tee gpurun_out/n_summary.txt
+echo "verified suite rc=$?" | tee -a gpurun_out/n_summary.txt
 
 # 2. the unverified groups, each in its own subprocess (logs: gpurun_out/unverified_<group>.log)
 timeout 1100 python -m pytest tests/test_zz_gpu_unverified.py -q -rxX > gpurun_out/n_tests_unverified.log 2>&1

@@ -9,6 +9,7 @@
 // Every result line goes to stdout and to gpurun_out/hwcheck.txt as soon as it is known.
 //   make -C monocular_depth_estimation_b200/csrc hwcheck
 //   tools/hwcheck            (on a B200)          tools/hwcheck --dry DIR   (no GPU: dumps inputs + references to DIR)
+//   tools/hwcheck --bench    (on a B200: CUDA-event timings of the opt-in kernels at config-2 sizes, a few seconds)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -464,6 +465,116 @@ static int run_adam() {
   return 0;
 }
 
+static int init_device_quiet();
+// =====================================================================================================
+// --bench: CUDA-event timings of the opt-in kernels at config-2 sizes (seconds of GPU time; one child process per
+// setting because the switches are read once per process)
+// =====================================================================================================
+static float time_ms(cudaEvent_t e0, cudaEvent_t e1) {
+  float ms = 0;
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  return ms;
+}
+static int bench_ln(int T, int C) {
+  if (init_device_quiet()) return 1;
+  float *x = nullptr, *y = nullptr, *g = nullptr, *b = nullptr, *st = nullptr;
+  CK(cudaMalloc(&x, static_cast<size_t>(T) * C * 4));
+  CK(cudaMalloc(&y, static_cast<size_t>(T) * C * 4));
+  CK(cudaMalloc(&g, C * 4));
+  CK(cudaMalloc(&b, C * 4));
+  CK(cudaMalloc(&st, static_cast<size_t>(T) * 8));
+  CK(cudaMemset(x, 0, static_cast<size_t>(T) * C * 4));
+  CK(cudaMemset(g, 0, C * 4));
+  CK(cudaMemset(b, 0, C * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int dt = 0; dt < 2; ++dt) {  // output bf16 (the in-block LayerNorms) and fp32
+    for (int i = 0; i < 3; ++i) crf_layernorm_fwd(x, g, b, 1e-5f, y, dt == 0 ? CRF_DT_BF16 : CRF_DT_F32, st, T, C, 0, nullptr);
+    cudaEventRecord(e0);
+    const int it = 20;
+    for (int i = 0; i < it; ++i) crf_layernorm_fwd(x, g, b, 1e-5f, y, dt == 0 ? CRF_DT_BF16 : CRF_DT_F32, st, T, C, 0, nullptr);
+    cudaEventRecord(e1);
+    const float ms = time_ms(e0, e1) / it;
+    const double bytes = static_cast<double>(T) * C * (4 + (dt == 0 ? 2 : 4));
+    say("bench layernorm_fwd T%d C%d out=%s CRF_LN_ROWS=%s: %.2f us, %.0f GB/s", T, C, dt == 0 ? "bf16" : "f32",
+        getenv("CRF_LN_ROWS") ? getenv("CRF_LN_ROWS") : "1", ms * 1e3, bytes / ms / 1e6);
+  }
+  return 0;
+}
+static int bench_adam(long long n_total, int n_tensors) {
+  if (init_device_quiet()) return 1;
+  const long long n = n_total / n_tensors;
+  std::vector<crf_adam_tensor> rec(n_tensors);
+  for (int i = 0; i < n_tensors; ++i) {
+    float* buf[4];
+    for (auto& p : buf) {
+      CK(cudaMalloc(&p, n * 4));
+      CK(cudaMemset(p, 0, n * 4));
+    }
+    rec[i] = {buf[0], buf[1], buf[2], buf[3], n};
+  }
+  float* step = nullptr;
+  CK(cudaMalloc(&step, 4));
+  CK(cudaMemset(step, 0, 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 2; ++i) crf_adam_step(rec.data(), n_tensors, 16384, 1e-4f, 0.9f, 0.999f, 1e-8f, 0.f, step, 0, nullptr);
+  cudaEventRecord(e0);
+  const int it = 10;
+  for (int i = 0; i < it; ++i) crf_adam_step(rec.data(), n_tensors, 16384, 1e-4f, 0.9f, 0.999f, 1e-8f, 0.f, step, 0, nullptr);
+  cudaEventRecord(e1);
+  const float ms = time_ms(e0, e1) / it;
+  say("bench adam_step %lld parameters in %d tensors: %.1f us, %.0f GB/s (28 B per parameter)", n * n_tensors, n_tensors,
+      ms * 1e3, 28.0 * n * n_tensors / ms / 1e6);
+  return 0;
+}
+static int bench_attn(const AttnCase& c) {
+  if (init_device_quiet()) return 1;
+  const int C = c.C, T = c.B * c.H * c.W;
+  crf::WindowGeom gm(c.H, c.W, 7, c.shift);
+  const int nWin = c.B * gm.nW;
+  crf_block_desc d;
+  memset(&d, 0, sizeof(d));
+  d.B = c.B; d.H = c.H; d.W = c.W; d.C = C; d.num_heads = c.nH; d.window = 7; d.shift = c.shift; d.training = 1;
+  d.x_dtype = CRF_DT_F32; d.v_dtype = CRF_DT_BF16; d.v_preconverted = 1;
+  d.x_stride_b = static_cast<int64_t>(c.H) * c.W * C; d.x_stride_t = C; d.x_stride_c = 1;
+  d.v_stride_b = d.x_stride_b; d.v_stride_h = static_cast<int64_t>(c.W) * C; d.v_stride_w = C; d.v_stride_c = 1;
+  uint16_t *qk, *vb, *o, *dout, *dqk;
+  float *bias, *table, *lse, *dv, *dt, *db;
+  CK(cudaMalloc(&qk, static_cast<size_t>(T) * 2 * C * 2)); CK(cudaMemset(qk, 0, static_cast<size_t>(T) * 2 * C * 2));
+  CK(cudaMalloc(&vb, static_cast<size_t>(T) * C * 2));     CK(cudaMemset(vb, 0, static_cast<size_t>(T) * C * 2));
+  CK(cudaMalloc(&o, static_cast<size_t>(T) * C * 2));
+  CK(cudaMalloc(&dout, static_cast<size_t>(T) * C * 2));   CK(cudaMemset(dout, 0, static_cast<size_t>(T) * C * 2));
+  CK(cudaMalloc(&dqk, static_cast<size_t>(T) * 2 * C * 2));
+  CK(cudaMalloc(&bias, 2 * C * 4));                         CK(cudaMemset(bias, 0, 2 * C * 4));
+  CK(cudaMalloc(&table, 169 * c.nH * 4));                   CK(cudaMemset(table, 0, 169 * c.nH * 4));
+  CK(cudaMalloc(&lse, static_cast<size_t>(nWin) * c.nH * 64 * 4));
+  CK(cudaMalloc(&dv, static_cast<size_t>(T) * C * 4));
+  CK(cudaMalloc(&dt, 169 * c.nH * 4));                      CK(cudaMemset(dt, 0, 169 * c.nH * 4));
+  CK(cudaMalloc(&db, 2 * C * 4));                           CK(cudaMemset(db, 0, 2 * C * 4));
+  const float scale = 1.0f / sqrtf(static_cast<float>(C / c.nH));
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  for (int i = 0; i < 2; ++i) {
+    if (crf_attn_fwd(&d, qk, vb, bias, scale, table, nullptr, 0, o, lse, nullptr)) { say("bench attn: %s", crf_last_error()); return 1; }
+    crf_attn_bwd(&d, qk, vb, bias, scale, table, nullptr, 0, lse, dout, dqk, dv, 0, dt, db, nullptr);
+  }
+  const int it = 5;
+  cudaEventRecord(e0);
+  for (int i = 0; i < it; ++i) crf_attn_fwd(&d, qk, vb, bias, scale, table, nullptr, 0, o, lse, nullptr);
+  cudaEventRecord(e1);
+  for (int i = 0; i < it; ++i) crf_attn_bwd(&d, qk, vb, bias, scale, table, nullptr, 0, lse, dout, dqk, dv, 0, dt, db, nullptr);
+  cudaEventRecord(e2);
+  const float f = time_ms(e0, e1) / it, b = time_ms(e1, e2) / it;
+  const double tc = static_cast<double>(T) * C;
+  say("bench attn B%d %dx%d C%d heads %d (head_dim %d) shift %d: fwd %.1f us (%.0f GB/s algorithmic), bwd %.1f us (%.0f GB/s)",
+      c.B, c.H, c.W, C, c.nH, C / c.nH, c.shift, f * 1e3, 8.0 * tc / f / 1e6, b * 1e3, 16.0 * tc / b / 1e6);
+  return 0;
+}
+
 static int init_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -474,6 +585,8 @@ static int init_device() {
   cudaFree(0);
   return 0;
 }
+
+static int init_device_quiet() { return init_device(); }
 
 static const AttnCase kCases[] = {
     {2, 9, 10, 64, 2, 3},     // head_dim 32: the verified kernels -- validates this harness
@@ -526,6 +639,32 @@ int main(int argc, char** argv) {
   if (system("mkdir -p gpurun_out") != 0) return 1;
   g_log = fopen("gpurun_out/hwcheck.txt", "a");
   if (argc >= 3 && strcmp(argv[1], "--group") == 0) return run_group(atoi(argv[2]));
+  if (argc >= 2 && strcmp(argv[1], "--bench") == 0) {
+    // config-2 sizes; every setting in its own child (env switches are read once per process), one after the other
+    struct Job { int kind; const char* rows; AttnCase c; };
+    const Job jobs[] = {
+        {0, "1", {}}, {0, "4", {}}, {0, "2", {}},                       // LayerNorm forward, 1/4 scale, rows per warp
+        {1, "1", {}},                                                   // Adam over 45 M parameters
+        {2, "1", {8, 120, 160, 128, 4, 3}},                             // attention, head_dim 32 (tuned kernels)
+        {2, "1", {8, 120, 160, 128, 2, 3}}, {2, "1", {8, 120, 160, 128, 1, 3}},   // head_dim 64, 128 at the 1/4 scale
+        {2, "1", {8, 30, 40, 512, 8, 3}}, {2, "1", {8, 30, 40, 512, 4, 3}},       // head_dim 64, 128 at the 1/16 scale
+    };
+    for (const Job& j : jobs) {
+      const pid_t pid = fork();
+      if (pid == 0) {
+        setenv("CRF_LN_ROWS", j.rows, 1);
+        int rc = 0;
+        if (j.kind == 0) rc = bench_ln(153600, 128) | bench_ln(38400, 256);
+        else if (j.kind == 1) rc = bench_adam(45000000LL, 300);
+        else rc = bench_attn(j.c);
+        _exit(rc);
+      }
+      int st = 0;
+      waitpid(pid, &st, 0);
+    }
+    say("hwcheck --bench finished");
+    return 0;
+  }
   // all groups at once, each in its own process (no CUDA call has been made in the parent)
   pid_t pids[4];
   for (int grp = 0; grp < 4; ++grp) {
