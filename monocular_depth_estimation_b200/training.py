@@ -129,6 +129,55 @@ def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
     return int(ck.get("epoch", 0)), ck.get("loss")
 
 
+def synthetic_batches(n_batches, batch, height=480, width=640, seed=0, pin=None):
+    """Stand-in for the reference's loader (src/data.py:179, consumed at src/train.py:86-89): yields dicts
+    {'image': (B, 3, H, W) in [0, 1], 'depth': (B, 1, H, W)} of host tensors, NYU-shaped, pinned when CUDA is present."""
+    gen = torch.Generator().manual_seed(seed)
+    pin = torch.cuda.is_available() if pin is None else pin
+    for _ in range(n_batches):
+        sample = {"image": torch.rand(batch, 3, height, width, generator=gen),
+                  "depth": torch.rand(batch, 1, height, width, generator=gen) * 9.0 + 1.0}
+        yield {k: (t.pin_memory() if pin else t) for k, t in sample.items()}
+
+
+def prefetch_to_device(batches, device, memory_format=torch.contiguous_format):
+    """Iterate `batches` (dicts of host tensors, as the reference loop's `sample_batched`) one step ahead: the
+    host -> device copy of batch i+1 runs on a copy stream while the caller computes on batch i (what bench.py's `e2e`
+    measures).  On a CPU device the samples pass through unchanged."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        for sample in batches:
+            yield sample
+        return
+    copy_stream = torch.cuda.Stream(device)
+
+    def stage(sample):
+        with torch.cuda.stream(copy_stream):
+            out = {}
+            for k, t in sample.items():
+                fmt = memory_format if t.dim() == 4 and t.shape[1] > 1 else torch.contiguous_format
+                out[k] = t.to(device, non_blocking=True, memory_format=fmt)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return out, ev
+
+    it = iter(batches)
+    nxt = None
+    for sample in it:
+        nxt = stage(sample)
+        break
+    while nxt is not None:
+        cur, ev = nxt
+        nxt = None
+        for sample in it:
+            nxt = stage(sample)
+            break
+        torch.cuda.current_stream(device).wait_event(ev)
+        for t in cur.values():   # the consumer's stream now owns these buffers
+            t.record_stream(torch.cuda.current_stream(device))
+        yield cur
+
+
 class LibAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr) of the reference loop (src/train.py:41, :108) as the library's multi-tensor step
     (crf_adam_step: 80 tensors per launch, pointers passed as launch arguments) instead of torch's multi-tensor launches;

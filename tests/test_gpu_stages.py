@@ -463,3 +463,17 @@ def test_lib_adam_matches_torch_adam():
     oa2.step()
     torch.cuda.synchronize()
     assert float(oa2.state[ours[0]]["step"]) == 7.0
+
+
+@pytest.mark.skipif(os.environ.get("CRF_TEST_UNVERIFIED") != "1",
+                    reason="not yet run on hardware: runs from tests/test_zz_gpu_unverified.py (CRF_TEST_UNVERIFIED=1)")
+def test_prefetch_loader_cuda():
+    """training.prefetch_to_device: same samples, same order, on the device (channels-last images), copies overlapped."""
+    from monocular_depth_estimation_b200 import training as TR
+    host = list(TR.synthetic_batches(4, 2, 32, 48, seed=3))
+    got = list(TR.prefetch_to_device(iter(host), DEV, memory_format=torch.channels_last))
+    torch.cuda.synchronize()
+    assert len(got) == 4
+    for h, g in zip(host, got):
+        assert g["image"].is_cuda and g["image"].is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(g["image"].cpu(), h["image"]) and torch.equal(g["depth"].cpu(), h["depth"])

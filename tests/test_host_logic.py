@@ -120,3 +120,18 @@ def test_checkpoint_format_round_trip(tmp_path):
     raw["model_state_dict"] = {"module." + k: v for k, v in raw["model_state_dict"].items()}
     torch.save(raw, path)
     TR.load_checkpoint(path, pkg.NewCRF(input_dim=8, embed_dim=64, v_dim=8, num_heads=2))
+
+
+def test_synthetic_loader_and_prefetch_on_cpu():
+    """The loader stand-in yields the reference loop's sample dicts (src/train.py:86-89); on a CPU device the prefetcher
+    is a pass-through that preserves order and count."""
+    from monocular_depth_estimation_b200 import training as TR
+    a = list(TR.synthetic_batches(3, 2, 32, 48, seed=1, pin=False))
+    b = list(TR.prefetch_to_device(TR.synthetic_batches(3, 2, 32, 48, seed=1, pin=False), "cpu"))
+    assert len(a) == len(b) == 3
+    for x, y in zip(a, b):
+        assert sorted(x) == ["depth", "image"]
+        assert x["image"].shape == (2, 3, 32, 48) and x["depth"].shape == (2, 1, 32, 48)
+        assert torch.equal(x["image"], y["image"]) and torch.equal(x["depth"], y["depth"])
+        assert 0 <= float(x["image"].min()) and float(x["image"].max()) <= 1 and float(x["depth"].min()) >= 1
+    assert list(TR.prefetch_to_device(iter(()), "cpu")) == []

@@ -33,7 +33,7 @@ GROUPS = {   # name: (pytest -k expression, extra environment)
     "ln_multirow": ("test_ln_fwd or test_layer_norm_standalone or test_colsum_cast_convert or test_config1_block",
                     {"CRF_LN_ROWS": "4"}),
     # Group D -- new kernel outside the block: the one-launch Adam step (crf_adam_step, training.LibAdam)
-    "lib_adam": ("test_lib_adam_matches_torch_adam", {}),
+    "lib_adam": ("test_lib_adam_matches_torch_adam or test_prefetch_loader_cuda", {}),
 }
 
 
