@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CRF_ABI_VERSION 1
+#define CRF_ABI_VERSION 2
 
 enum { CRF_DT_F32 = 0, CRF_DT_BF16 = 1 };
 
@@ -240,7 +240,8 @@ int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, 
  *   chunk_elems  elements one CTA updates (multiple of 4, >= 1024; 16384 is a good value)
  *   step     DEVICE float: number of steps taken so far; the update uses step + 1 and the call then increments it
  *            (so a CUDA graph that captured the call keeps counting on replay)
- * Verified against the host update on a B200 (profiles/r01_hwcheck.txt); not yet used by default (bench.py --lib-adam). */
+ * Hyper-parameters are doubles (torch keeps them as Python floats and derives 1 - beta, the bias corrections and
+ * lr / bc1 in double before rounding once to fp32; ABI version 2 changed them from float). */
 typedef struct crf_adam_tensor {
   float* p;        /* parameter, updated in place */
   const float* g;  /* gradient */
@@ -248,8 +249,8 @@ typedef struct crf_adam_tensor {
   float* v;        /* exp_avg_sq, updated in place */
   int64_t n;       /* elements */
 } crf_adam_tensor;
-int crf_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, float* step, int device, void* stream);
+int crf_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, float* step, int device, void* stream);
 /* out[n] += sum_t g[t, n], g bf16 (T, N) contiguous, N % 4 == 0 */
 int crf_colsum_bf16(const void* g, float* out, int T, int N, int device, void* stream);
 /* f32 -> bf16 contiguous */

@@ -85,7 +85,7 @@ _lib = None
 
 
 def _declare(lib):
-    vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+    vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
     lib.crf_last_error.restype = C.c_char_p
     lib.crf_last_error.argtypes = []
     lib.crf_abi_version.restype = i32
@@ -114,7 +114,7 @@ def _declare(lib):
     lib.crf_pixel_shuffle_nhwc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_colsum_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.crf_cast_bf16.argtypes = [vp, vp, i64, i32, vp]
-    lib.crf_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, f32, f32, f32, f32, f32, vp, i32, vp]
+    lib.crf_adam_step.argtypes = [C.POINTER(AdamTensor), i32, i32, f64, f64, f64, f64, f64, vp, i32, vp]
     lib.crf_attn_fwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp]
     lib.crf_attn_bwd.argtypes = [C.POINTER(BlockDesc), vp, vp, vp, f32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:

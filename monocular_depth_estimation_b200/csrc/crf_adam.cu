@@ -31,12 +31,15 @@ struct AdamBatch {
 static_assert(sizeof(AdamBatch) <= 4000, "kernel-argument budget");
 
 __global__ void __launch_bounds__(kAdamThreads)
-adam_multi_kernel(const __grid_constant__ AdamBatch B, int chunk_elems, float lr, float b1, float b2, float eps,
-                  float wd, const float* __restrict__ step) {
+adam_multi_kernel(const __grid_constant__ AdamBatch B, int chunk_elems, double lr, double b1, double b2, double eps,
+                  double wd, const float* __restrict__ step) {
   int ti = 0;
   while (ti + 1 < B.count && static_cast<int>(blockIdx.x) >= B.chunk_end[ti]) ++ti;   // uniform per CTA, <= 80 steps
   const int chunk = static_cast<int>(blockIdx.x) - (ti > 0 ? B.chunk_end[ti - 1] : 0);
-  const AdamCoef c = adam_coef(lr, b1, b2, eps, wd, *step + 1.0f);
+  __shared__ AdamCoef c_sh;   // double-precision pow / sqrt once per CTA, not once per thread
+  if (threadIdx.x == 0) c_sh = adam_coef(lr, b1, b2, eps, wd, static_cast<double>(*step) + 1.0);
+  __syncthreads();
+  const AdamCoef c = c_sh;
   const long long lo = static_cast<long long>(chunk) * chunk_elems;
   long long hi = lo + chunk_elems;
   if (hi > B.n[ti]) hi = B.n[ti];
@@ -82,13 +85,13 @@ __global__ void adam_count_kernel(float* step) { *step += 1.0f; }
 
 }  // namespace
 
-int launch_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, float lr, float b1, float b2,
-                     float eps, float wd, float* step, cudaStream_t st) {
+int launch_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, double lr, double b1, double b2,
+                     double eps, double wd, float* step, cudaStream_t st) {
   CRF_CHECK(tensors != nullptr && step != nullptr, "crf_adam_step: null pointer");
   CRF_CHECK(n_tensors > 0, "crf_adam_step: no tensors");
   CRF_CHECK(chunk_elems >= 1024 && chunk_elems % 4 == 0, "crf_adam_step: chunk_elems=%d must be a multiple of 4, >= 1024",
             chunk_elems);
-  CRF_CHECK(b1 >= 0.f && b1 < 1.f && b2 >= 0.f && b2 < 1.f && eps >= 0.f && lr >= 0.f && wd >= 0.f,
+  CRF_CHECK(b1 >= 0. && b1 < 1. && b2 >= 0. && b2 < 1. && eps >= 0. && lr >= 0. && wd >= 0.,
             "crf_adam_step: bad hyper-parameters");
   double total = 0;
   for (int i = 0; i < n_tensors; ++i) {

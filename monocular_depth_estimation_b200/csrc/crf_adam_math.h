@@ -17,19 +17,21 @@ struct AdamCoef {
   float b1, b2, one_minus_b1, one_minus_b2, step_size, sqrt_bc2, eps, wd;
 };
 
-// t = number of the step being taken (1 for the first).
-CRF_HD AdamCoef adam_coef(float lr, float b1, float b2, float eps, float wd, float t) {
+// t = number of the step being taken (1 for the first).  The hyper-parameters are Python doubles in torch.optim.Adam and
+// torch derives 1 - beta, the bias corrections and lr / bc1 in double before rounding once to the parameter's precision
+// (with fp32 arithmetic 1 - 0.999f is 0.0009999871, a 1.3e-5 relative bias on every exp_avg_sq): same here.
+CRF_HD AdamCoef adam_coef(double lr, double b1, double b2, double eps, double wd, double t) {
   AdamCoef c;
-  c.b1 = b1;
-  c.b2 = b2;
-  c.one_minus_b1 = 1.0f - b1;
-  c.one_minus_b2 = 1.0f - b2;
-  const float bc1 = 1.0f - powf(b1, t);
-  const float bc2 = 1.0f - powf(b2, t);
-  c.step_size = lr / bc1;
-  c.sqrt_bc2 = sqrtf(bc2);
-  c.eps = eps;
-  c.wd = wd;
+  c.b1 = static_cast<float>(b1);
+  c.b2 = static_cast<float>(b2);
+  c.one_minus_b1 = static_cast<float>(1.0 - b1);
+  c.one_minus_b2 = static_cast<float>(1.0 - b2);
+  const double bc1 = 1.0 - pow(b1, t);
+  const double bc2 = 1.0 - pow(b2, t);
+  c.step_size = static_cast<float>(lr / bc1);
+  c.sqrt_bc2 = static_cast<float>(sqrt(bc2));
+  c.eps = static_cast<float>(eps);
+  c.wd = static_cast<float>(wd);
   return c;
 }
 

@@ -510,8 +510,8 @@ int crf_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, 
   CRF_CHECK(guard.ok, "cannot select device %d", device);
   return launch_pixel_shuffle_nhwc(src, dst, dtype, B, H, W, C, inverse, static_cast<cudaStream_t>(stream));
 }
-int crf_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, float* step, int device, void* stream) {
+int crf_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, float* step, int device, void* stream) {
   DeviceGuard guard(device);
   CRF_CHECK(guard.ok, "cannot select device %d", device);
   return launch_adam_step(tensors, n_tensors, chunk_elems, lr, beta1, beta2, eps, weight_decay, step,

@@ -87,8 +87,8 @@ int launch_depth_loss_bwd(const void* pred, int pred_dtype, const float* tgt, co
                           int n_img, int H, int W, void* dpred, cudaStream_t st);
 int launch_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, int inverse,
                               cudaStream_t st);
-int launch_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, float lr, float b1, float b2,
-                     float eps, float wd, float* step, cudaStream_t st);
+int launch_adam_step(const crf_adam_tensor* tensors, int n_tensors, int chunk_elems, double lr, double b1, double b2,
+                     double eps, double wd, float* step, cudaStream_t st);
 int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st);
 int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
 int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long long n[4], cudaStream_t st);

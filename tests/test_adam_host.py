@@ -14,10 +14,10 @@ CSRC = os.path.join(ROOT, "monocular_depth_estimation_b200", "csrc")
 
 SHIM = r"""
 #include "crf_adam_math.h"
-extern "C" void adam_steps(float* p, const float* g, float* m, float* v, int n, int steps, float lr, float b1, float b2,
-                           float eps, float wd) {
+extern "C" void adam_steps(float* p, const float* g, float* m, float* v, int n, int steps, double lr, double b1, double b2,
+                           double eps, double wd) {
   for (int t = 1; t <= steps; ++t) {
-    const crf::AdamCoef c = crf::adam_coef(lr, b1, b2, eps, wd, (float)t);
+    const crf::AdamCoef c = crf::adam_coef(lr, b1, b2, eps, wd, (double)t);
     for (int i = 0; i < n; ++i) crf::adam_update(c, p[i], g[(t - 1) * n + i], m[i], v[i]);
   }
 }
@@ -32,7 +32,7 @@ def shim(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", CSRC, str(src), "-o", str(so)], check=True)
     lib = ctypes.CDLL(str(so))
     fp = ctypes.POINTER(ctypes.c_float)
-    lib.adam_steps.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 5
+    lib.adam_steps.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 5
     lib.adam_steps.restype = None
     return lib
 
@@ -63,8 +63,8 @@ def test_element_update_matches_torch_adam(shim, wd):
     assert np.abs(upd - upd_ref).sum() <= 2e-4 * np.abs(upd_ref).sum()
     # per-element scale of the effective gradient g + wd * p (the moments are sums with cancellation)
     gs = np.abs(g).max(axis=0) + wd * (np.abs(p0.numpy()) + 1e-2)
-    assert (np.abs(m - st["exp_avg"].numpy()) <= 1e-5 * np.abs(m) + 2e-6 * gs).all()
-    assert (np.abs(v - st["exp_avg_sq"].numpy()) <= 1e-5 * np.abs(v) + 2e-6 * gs * gs).all()
+    assert (np.abs(m - st["exp_avg"].numpy()) <= 2e-6 * np.abs(m) + 2e-6 * gs).all()
+    assert (np.abs(v - st["exp_avg_sq"].numpy()) <= 2e-6 * np.abs(v) + 2e-6 * gs * gs).all()
 
 
 def test_chunk_counts_cover_every_element_once():

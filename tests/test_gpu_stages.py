@@ -347,22 +347,16 @@ def test_attn_fwd(B, H, W, C, nH, shift):
     _check(lse[:, :, :49], ref_lse, 1e-4, "attn_fwd.lse")
 
 
-# head_dim 64 / 128 (crf_attn_wide.cu): the kernels are verified on hardware through tools/hwcheck (profiles/r01_hwcheck.txt);
-# these pytest cases were written after the GPU budget was spent and have not run yet -- tests/test_zz_gpu_unverified.py runs
-# them in a subprocess with CRF_TEST_UNVERIFIED=1; a plain `pytest -m gpu` skips them.
-wide_only = pytest.mark.skipif(os.environ.get("CRF_TEST_UNVERIFIED") != "1",
-                               reason="not yet run on hardware: runs from tests/test_zz_gpu_unverified.py (CRF_TEST_UNVERIFIED=1)")
+# head_dim 64 / 128 (crf_attn_wide.cu; BASELINE.json configs[2])
 WIDE_CASES = [(1, 7, 7, 64, 1, 0), (2, 9, 10, 64, 1, 3), (1, 14, 14, 128, 2, 0), (1, 15, 20, 128, 1, 3),
               (3, 30, 40, 256, 4, 3), (2, 15, 20, 256, 2, 0), (1, 21, 16, 512, 4, 3), (2, 23, 17, 512, 8, 3)]
 
 
-@wide_only
 @pytest.mark.parametrize("B,H,W,C,nH,shift", WIDE_CASES)
 def test_attn_fwd_wide(B, H, W, C, nH, shift):
     test_attn_fwd(B, H, W, C, nH, shift)
 
 
-@wide_only
 @pytest.mark.parametrize("B,H,W,C,nH,shift", WIDE_CASES)
 def test_attn_bwd_wide(B, H, W, C, nH, shift):
     test_attn_bwd(B, H, W, C, nH, shift)
@@ -426,8 +420,6 @@ def test_attn_bwd(B, H, W, C, nH, shift):
     assert d_bias[:C].abs().max() == 0
 
 
-@pytest.mark.skipif(os.environ.get("CRF_TEST_UNVERIFIED") != "1",
-                    reason="not yet run on hardware: runs from tests/test_zz_gpu_unverified.py (CRF_TEST_UNVERIFIED=1)")
 def test_lib_adam_matches_torch_adam():
     """training.LibAdam (crf_adam_step: one launch for all tensors, device-side step counter) against torch.optim.Adam
     on identical parameters / gradients over several steps, including odd sizes, an unaligned view and a state_dict
@@ -465,8 +457,6 @@ def test_lib_adam_matches_torch_adam():
     assert float(oa2.state[ours[0]]["step"]) == 7.0
 
 
-@pytest.mark.skipif(os.environ.get("CRF_TEST_UNVERIFIED") != "1",
-                    reason="not yet run on hardware: runs from tests/test_zz_gpu_unverified.py (CRF_TEST_UNVERIFIED=1)")
 def test_prefetch_loader_cuda():
     """training.prefetch_to_device: same samples, same order, on the device (channels-last images), copies overlapped."""
     from monocular_depth_estimation_b200 import training as TR

@@ -435,7 +435,7 @@ static int run_adam() {
       float* dg = dgbase[i] + (i == 3 ? 1 : 0);   // tensor 3: 4-byte-aligned gradient view
       CK(cudaMemcpy(dg, g.data(), g.size() * 4, cudaMemcpyHostToDevice));
       rec[i] = {dp[i], dg, dm[i], dv[i], sizes[i]};
-      const crf::AdamCoef c = crf::adam_coef(lr, b1, b2, eps, 0.f, static_cast<float>(step));
+      const crf::AdamCoef c = crf::adam_coef(lr, b1, b2, eps, 0.0, static_cast<double>(step));
       for (int k = 0; k < sizes[i]; ++k) crf::adam_update(c, p[i][k], g[k], m[i][k], v[i][k]);
     }
     if (crf_adam_step(rec, 4, 16384, lr, b1, b2, eps, 0.f, dstep, 0, nullptr)) {
