@@ -50,7 +50,11 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU (weak scaling)")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--ref-batch", type=int, default=2, help="images per CPU reference step (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=0,
+                    help="images per CPU reference step; 0 (default): the same batch as our arm (--batch)")
+    ap.add_argument("--regions", type=int, default=5,
+                    help="timed regions of exactly --steps steps each; `value` is the MEDIAN region (step time is bimodal "
+                         "across repetitions, DESIGN.md 8), all regions are listed in `regions_ms_per_step`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel timing table (JSON) to this file")
     ap.add_argument("--cuda-graph", type=int, default=2,
@@ -63,9 +67,9 @@ def parse_args():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="BASELINE configs[3]: fixed global batch (64) sharded over the ranks, i.e. strong scaling; "
                          "0 (default): --batch images per GPU, weak scaling")
-    ap.add_argument("--gpu-eager-baseline", action="store_true",
-                    help="N=1: also time the oracle port of the reference's eager PyTorch path on this GPU (reported as "
-                         "gpu_eager_baseline; SURVEY.md 8d); off by default")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true",
+                    help="N=1: skip timing the reference's eager PyTorch path on this GPU (gpu_eager_baseline / "
+                         "vs_gpu_eager; SURVEY.md 8d, BASELINE.md 3)")
     ap.add_argument("--lib-adam", action="store_true",
                     help="use the library's one-launch Adam step (crf_adam_step) instead of torch's fused Adam; opt-in")
     ap.add_argument("--ddp-grad-bf16", action="store_true",
@@ -161,13 +165,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 3))
-    r = cpu_reference_run(args.ref_batch, args.height, args.width, steps, warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    ref_batch = args.ref_batch or args.batch
+    r = cpu_reference_run(ref_batch, args.height, args.width, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "MobileNetV3-large + NeWCRFs decoder train step (fwd+loss+bwd+Adam), "
-                                   f"{args.height}x{args.width}, host CPU, batch {args.ref_batch} per step"},
+                                   f"{args.height}x{args.width}, host CPU, batch {ref_batch} per step "
+                                   "(BASELINE.json configs[1])",
+                       "global_batch": ref_batch, "parallelism": "host CPU, 1 process",
+                       "arm": "oracle port of the reference's PyTorch CPU path (the Python reference cannot travel to "
+                              "the GPU box; the port is pinned to the unmodified reference by tests/test_oracle_golden.py)"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

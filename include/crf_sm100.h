@@ -198,6 +198,23 @@ int crf_gemm(const crf_gemm_args* a, void* stream);
 /* workspace a CRF_EPI_SPLITK_F32 GEMM of this shape wants (0 when it runs as a single split) */
 size_t crf_gemm_workspace_bytes(int M, int N, int K, int device);
 
+/* The MLP half of a block in ONE kernel (C = 128 or 256):  y = x1 + fc2(GELU(fc1(LayerNorm(x1))))
+ * (replaces `x + self.mlp(self.norm2(x))`, /root/reference/src/newcrf_layers.py:255, Mlp.forward :21-27).
+ * The 4C-wide hidden activation stays on chip between fc1 and fc2 (TMEM -> registers -> shared memory).
+ *   x1, y        f32 (T, C) contiguous (y may not alias x1)
+ *   w1_bf16      bf16 (4C, C) = fc1.weight;  w2_bf16 bf16 (C, 4C) = fc2.weight;  b1 (4C), b2 (C), norm_w/norm_b (C) f32
+ *   training=1   also writes what the backward kernels read: xn2 bf16 (T, C), stats f32 (T, 2) = (mean, rstd),
+ *                pre bf16 (T, 4C) (fc1 output + bias), act bf16 (T, 4C) (GELU of it); training=0: those may be NULL */
+typedef struct crf_mlp_args {
+  const float* x1; float* y;
+  const void* w1_bf16; const void* w2_bf16;
+  const float* b1; const float* b2; const float* norm_w; const float* norm_b;
+  void* xn2; float* stats; void* pre; void* act;
+  float eps;
+  int32_t T, C, training, device;
+} crf_mlp_args;
+int crf_mlp_fwd(const crf_mlp_args* a, void* stream);
+
 /* LayerNorm forward over channels with a layout change: x (B, T_img, C) with arbitrary strides ->
  * xn bf16 (T, C), stats f32 (T, 2) = (mean, rstd), optional contiguous f32 copy of x. */
 int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, int B, int T_img, int C,

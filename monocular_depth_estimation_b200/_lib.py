@@ -26,7 +26,7 @@ EPI_SPLITK_F32 = 5
 EXPORTED_SYMBOLS = (
     "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_timing_enable", "crf_timing_report", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
     "crf_layer_sizes", "crf_layer_fwd", "crf_layer_bwd",
-    "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_gemm_workspace_bytes", "crf_ln_fwd", "crf_ln_bwd",
+    "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_mlp_fwd", "crf_gemm_workspace_bytes", "crf_ln_fwd", "crf_ln_bwd",
     "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd", "crf_pixel_shuffle_nhwc",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd", "crf_adam_step",
 )
@@ -80,6 +80,17 @@ class GemmArgs(C.Structure):
     ]
 
 
+class MlpArgs(C.Structure):              # include/crf_sm100.h: crf_mlp_args
+    _fields_ = [
+        ("x1", C.c_void_p), ("y", C.c_void_p),
+        ("w1_bf16", C.c_void_p), ("w2_bf16", C.c_void_p),
+        ("b1", C.c_void_p), ("b2", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p),
+        ("xn2", C.c_void_p), ("stats", C.c_void_p), ("pre", C.c_void_p), ("act", C.c_void_p),
+        ("eps", C.c_float),
+        ("T", C.c_int32), ("C", C.c_int32), ("training", C.c_int32), ("device", C.c_int32),
+    ]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -103,6 +114,7 @@ def _declare(lib):
     lib.crf_window_scatter.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.crf_shift_mask.argtypes = [vp, i32, i32, i32, i32, vp]
     lib.crf_gemm.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.crf_mlp_fwd.argtypes = [C.POINTER(MlpArgs), vp]
     lib.crf_gemm_workspace_bytes.restype = sz
     lib.crf_gemm_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.crf_ln_fwd.argtypes = [vp, i32, i64, i64, i64, i32, i32, i32, vp, vp, f32, vp, vp, vp, i32, vp]

@@ -1,5 +1,7 @@
 // extern "C" entry points of libcrf_sm100.so (see include/crf_sm100.h) and the per-block orchestration:
 // which kernels run, in what order, on which slices of the caller-provided `saved` / workspace buffers.
+#include <stdlib.h>
+
 #include "crf_host.h"
 #include "crf_window.cuh"
 
@@ -16,6 +18,11 @@ struct SavedLayout {
 struct BwdLayout {
   size_t dyb, dhpre, dxn, dx1, dx1b, dob, dqk, partials, partials_bytes, total;
 };
+
+bool fused_mlp_enabled() {
+  static const bool on = [] { const char* e = getenv("CRF_FUSED_MLP"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
 
 bool x_is_plain(const crf_block_desc& d) {
   const int64_t T_img = static_cast<int64_t>(d.H) * d.W;
@@ -196,6 +203,18 @@ static int block_fwd_impl(const crf_block_desc* d, const crf_block_params* p, co
   if (gemm_fprop(S + L.attn_o, S + L.wb_proj, T, C, C, CRF_EPI_BIAS_RES_F32, S + L.x1, nullptr, p->proj_b, x_tok, 1.f,
                  0, d->device, st))
     return 1;
+  // LN2 + MLP + residual in one kernel where the fused kernel exists (C = 128, 256; CRF_FUSED_MLP=0 restores the
+  // three-kernel path below)
+  if (mlp_fused_supported(C) && fused_mlp_enabled()) {
+    crf_mlp_args m{};
+    m.x1 = reinterpret_cast<const float*>(S + L.x1); m.y = y;
+    m.w1_bf16 = S + L.wb_fc1; m.w2_bf16 = S + L.wb_fc2;
+    m.b1 = p->fc1_b; m.b2 = p->fc2_b; m.norm_w = p->norm2_w; m.norm_b = p->norm2_b;
+    m.xn2 = S + L.xn2; m.stats = reinterpret_cast<float*>(S + L.stats2);
+    m.pre = d->training ? S + L.pre : nullptr; m.act = S + L.act;
+    m.eps = p->ln_eps; m.T = T; m.C = C; m.training = d->training; m.device = d->device;
+    return launch_mlp_fused_fwd(m, st);
+  }
   // LN2
   if (launch_ln_fwd(S + L.x1, CRF_DT_F32, static_cast<int64_t>(d->H) * d->W * C, C, 1, d->B, d->H * d->W, C,
                     p->norm2_w, p->norm2_b, p->ln_eps, S + L.xn2, reinterpret_cast<float*>(S + L.stats2), nullptr, st))
@@ -457,6 +476,13 @@ int crf_gemm(const crf_gemm_args* a, void* stream) {
   DeviceGuard guard(a->device);
   CRF_CHECK(guard.ok, "cannot select device %d", a->device);
   return launch_gemm(*a, static_cast<cudaStream_t>(stream));
+}
+
+int crf_mlp_fwd(const crf_mlp_args* a, void* stream) {
+  CRF_CHECK(a != nullptr, "crf_mlp_fwd: null arguments");
+  DeviceGuard guard(a->device);
+  CRF_CHECK(guard.ok, "cannot select device %d", a->device);
+  return launch_mlp_fused_fwd(*a, static_cast<cudaStream_t>(stream));
 }
 
 int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, int B, int T_img, int C,

@@ -73,6 +73,29 @@ def gemm(A, B, M, N, K, *, a_major=0, b_major=0, epilogue=L.EPI_STORE_F32, out0,
     return out0
 
 
+def mlp_fwd(x1, norm_w, norm_b, w1_bf16, b1, w2_bf16, b2, eps=1e-5, training=True):
+    """Fused LayerNorm -> fc1 -> GELU -> fc2 -> + x1 (crf_mlp_fwd; C = 128 / 256).  x1: fp32 (T, C) contiguous.
+    Returns (y, xn2, stats, pre, act); the last four are None with training=False."""
+    T, Cd = x1.shape
+    dev = x1.device
+    y = torch.empty(T, Cd, dtype=torch.float32, device=dev)
+    xn2 = stats = pre = act = None
+    if training:
+        xn2 = torch.empty(T, Cd, dtype=torch.bfloat16, device=dev)
+        stats = torch.empty(T, 2, dtype=torch.float32, device=dev)
+        pre = torch.empty(T, 4 * Cd, dtype=torch.bfloat16, device=dev)
+        act = torch.empty(T, 4 * Cd, dtype=torch.bfloat16, device=dev)
+    a = L.MlpArgs()
+    a.x1, a.y = x1.data_ptr(), y.data_ptr()
+    a.w1_bf16, a.w2_bf16 = w1_bf16.data_ptr(), w2_bf16.data_ptr()
+    a.b1, a.b2, a.norm_w, a.norm_b = b1.data_ptr(), b2.data_ptr(), norm_w.data_ptr(), norm_b.data_ptr()
+    if training:
+        a.xn2, a.stats, a.pre, a.act = xn2.data_ptr(), stats.data_ptr(), pre.data_ptr(), act.data_ptr()
+    a.eps, a.T, a.C, a.training, a.device = eps, T, Cd, int(training), _dev(x1)
+    L.check(L.lib().crf_mlp_fwd(C.byref(a), _stream(x1)), "crf_mlp_fwd")
+    return y, xn2, stats, pre, act
+
+
 def ln_fwd(x, gamma, beta, eps=1e-5, want_copy=False):
     """x: logical (B, T_img, C) any strides -> (xn bf16 (B*T_img, C), stats (B*T_img, 2), copy or None)"""
     Bn, T_img, Cd = x.shape

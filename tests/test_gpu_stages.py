@@ -125,6 +125,55 @@ def test_gemm_epilogues():
 # ---------------------------------------------------------------------------------------------------------
 # LayerNorm / conversions / reductions
 # ---------------------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------
+# fused MLP half: LayerNorm-2 -> fc1 -> GELU -> fc2 -> + residual in one kernel (csrc/crf_mlp_fused.cu)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,C", [(128, 128), (300, 128), (1000, 128), (19200, 128), (153600, 128),
+                                 (77, 256), (1000, 256), (38400, 256)])
+@pytest.mark.parametrize("training", [True, False])
+def test_mlp_fused_fwd(T, C, training):
+    """y = x1 + fc2(gelu(fc1(LN(x1)))) (newcrf_layers.py:255, :21-27) against fp32 PyTorch on the same bf16-rounded
+    weights; the saved tensors (xn2, stats, pre, act) against the same reference; xn2 / stats BIT-EXACT against the
+    stand-alone LayerNorm kernel (same summation order), y against the unfused three-kernel path."""
+    ops, L = _ops(), _L()
+    g = torch.Generator(device="cpu").manual_seed(T + C)
+    x1 = (torch.randn(T, C, generator=g) * 1.5 + 0.3).to(DEV)
+    gam = (1.0 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    bet = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    w1, w2 = _rand_bf16(4 * C, C, seed=3, scale=C ** -0.5), _rand_bf16(C, 4 * C, seed=4, scale=(4 * C) ** -0.5)
+    b1 = (0.1 * torch.randn(4 * C, generator=g)).to(DEV)
+    b2 = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    y, xn2, stats, pre, act = ops.mlp_fwd(x1, gam, bet, w1, b1, w2, b2, eps=1e-5, training=training)
+    torch.cuda.synchronize()
+    # reference with the kernel's rounding points (xn2 and act are bf16 tensor-core operands)
+    xn_ref = F.layer_norm(x1, (C,), gam, bet, 1e-5)
+    pre_ref = xn_ref.to(torch.bfloat16).float() @ w1.float().t() + b1
+    act_ref = F.gelu(pre_ref)
+    y_ref = x1 + act_ref.to(torch.bfloat16).float() @ w2.float().t() + b2
+    _check(y, y_ref, 2e-3, "mlp_fused.y")
+    assert float((y - y_ref).abs().max()) < 2e-2 * float(y_ref.abs().max()), "mlp_fused.y max-abs"
+    # fp32 reference without any bf16 rounding: the bf16-I/O tolerance of the path
+    y_f32 = x1 + F.gelu(xn_ref @ w1.float().t() + b1) @ w2.float().t() + b2
+    _check(y, y_f32, 6e-3, "mlp_fused.y vs fp32")
+    if training:
+        _check(xn2.float(), xn_ref, 4e-3, "mlp_fused.xn2")
+        _check(pre.float(), pre_ref, 4e-3, "mlp_fused.pre")
+        _check(act.float(), act_ref, 5e-3, "mlp_fused.act")
+        xn_k, stats_k, _ = ops.ln_fwd(x1.view(1, T, C), gam, bet, 1e-5)
+        assert torch.equal(xn2, xn_k), "fused LayerNorm output differs from the stand-alone kernel"
+        assert torch.equal(stats, stats_k), "fused LayerNorm statistics differ from the stand-alone kernel"
+        # the unfused path on the same operands: fc1 (+GELU) and fc2 (+residual) through crf_gemm
+        pre_k = torch.empty(T, 4 * C, dtype=torch.bfloat16, device=DEV)
+        act_k = torch.empty(T, 4 * C, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(xn_k, w1, T, 4 * C, C, epilogue=L.EPI_BIAS_GELU, out0=pre_k, out1=act_k, bias=b1)
+        y_k = torch.empty(T, C, device=DEV)
+        ops.gemm(act_k, w2, T, C, 4 * C, epilogue=L.EPI_BIAS_RES_F32, out0=y_k, bias=b2, aux1=x1)
+        torch.cuda.synchronize()
+        _check(pre.float(), pre_k.float(), 1e-4, "mlp_fused.pre vs GEMM epilogue")   # same MMA sequence: expected bit-equal
+        _check(act.float(), act_k.float(), 1e-4, "mlp_fused.act vs GEMM epilogue")
+        _check(y, y_k, 1e-5, "mlp_fused.y vs unfused kernels")   # same products, different K-chunk summation order
+
+
 @pytest.mark.parametrize("C", [64, 128, 512, 1024])
 @pytest.mark.parametrize("layout", ["nchw_view", "contig", "bf16_nchw"])
 def test_ln_fwd(C, layout):
