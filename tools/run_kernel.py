@@ -30,7 +30,8 @@ def timed(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "block", "gemm", "gemms"])
+    ap.add_argument("what", choices=["attn", "block", "gemm", "gemms", "mlp"])
+    ap.add_argument("--infer", action="store_true", help="mlp: inference mode (no saved tensors)")
     ap.add_argument("--stage", type=int, default=0)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shift", type=int, default=3)
@@ -41,7 +42,30 @@ def main():
     B, dev = a.batch, torch.device("cuda:0")
     T = B * H * W
     torch.manual_seed(0)
-    if a.what == "attn":
+    if a.what == "mlp":   # fused LN2 + fc1 + GELU + fc2 + residual (csrc/crf_mlp_fused.cu); ops.mlp_fwd allocates outputs
+        x1 = torch.randn(T, C, device=dev)
+        gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        w1 = (torch.randn(4 * C, C, device=dev) * C ** -0.5).to(torch.bfloat16)
+        w2 = (torch.randn(C, 4 * C, device=dev) * (4 * C) ** -0.5).to(torch.bfloat16)
+        b1, b2 = torch.zeros(4 * C, device=dev), torch.zeros(C, device=dev)
+        import ctypes as Cc
+        y = torch.empty(T, C, device=dev)
+        xn2 = torch.empty(T, C, dtype=torch.bfloat16, device=dev)
+        stats = torch.empty(T, 2, device=dev)
+        pre = torch.empty(T, 4 * C, dtype=torch.bfloat16, device=dev)
+        act = torch.empty(T, 4 * C, dtype=torch.bfloat16, device=dev)
+        m = L.MlpArgs()
+        m.x1, m.y, m.w1_bf16, m.w2_bf16 = x1.data_ptr(), y.data_ptr(), w1.data_ptr(), w2.data_ptr()
+        m.b1, m.b2, m.norm_w, m.norm_b = b1.data_ptr(), b2.data_ptr(), gam.data_ptr(), bet.data_ptr()
+        m.xn2, m.stats, m.pre, m.act = xn2.data_ptr(), stats.data_ptr(), pre.data_ptr(), act.data_ptr()
+        m.eps, m.T, m.C, m.training, m.device = 1e-5, T, C, 0 if a.infer else 1, 0
+        st = Cc.c_void_p(torch.cuda.current_stream().cuda_stream)
+        run = lambda: L.check(L.lib().crf_mlp_fwd(Cc.byref(m), st), "crf_mlp_fwd")
+        ms = timed(run, a.iters)
+        byt = T * C * (8 + (0 if a.infer else 18))
+        print(f"mlp_fused T={T} C={C} {'infer' if a.infer else 'train'}: {ms * 1e3:.1f} us, "
+              f"{16.0 * T * C * C / ms / 1e9:.1f} TFLOP/s, {byt / ms / 1e6:.0f} GB/s")
+    elif a.what == "attn":
         qk = (torch.randn(T, 2 * C, device=dev) * 0.7).to(torch.bfloat16)
         vb = torch.randn(T, C, device=dev).to(torch.bfloat16)
         dout = torch.randn(T, C, device=dev).to(torch.bfloat16)
