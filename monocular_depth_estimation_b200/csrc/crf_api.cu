@@ -485,6 +485,9 @@ int crf_mlp_fwd(const crf_mlp_args* a, void* stream) {
   return launch_mlp_fused_fwd(*a, static_cast<cudaStream_t>(stream));
 }
 
+/* debug only (not in the public header): timeline of the last crf_mlp_fwd launch made with CRF_MLP_PROF=1 */
+int crf_debug_mlp_prof(long long* out, int n) { return mlp_debug_prof(out, n); }
+
 int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, int B, int T_img, int C,
                const float* gamma, const float* beta, float eps, void* xn_bf16, float* stats, float* x_copy,
                int device, void* stream) {

@@ -73,6 +73,7 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st);
 int launch_gemm_persistent(const crf_gemm_args& a, cudaStream_t st);  // -1: shape not eligible
 bool mlp_fused_supported(int C);                                      // crf_mlp_fused.cu: C = 128, 256
 int launch_mlp_fused_fwd(const crf_mlp_args& m, cudaStream_t st);
+int mlp_debug_prof(long long* out, int n);                            // CRF_MLP_PROF=1 timeline (debug)
 size_t gemm_splitk_workspace_bytes(int M, int N, int K, int device, int* splits_out);
 int launch_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st_, int64_t sc, int B, int T_img, int C,
                   const float* gamma, const float* beta, float eps, void* xn, float* stats, float* x_copy,

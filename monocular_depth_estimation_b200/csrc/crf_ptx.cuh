@@ -85,6 +85,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same, for waits that are expected to last microseconds (a role that works once per tile): back off with nanosleep
+// between polls so that the polling does not take issue slots from the warps doing the arithmetic.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("crf: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -211,6 +225,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM, same shape: thread i writes 32 consecutive fp32 columns of lane 32*(w%4)+i
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -315,6 +338,51 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   const float s = gelu_cdf(x);
   const float wp = fmaf(fmaf(-0.0035151686f, t, 0.22203402f), t, 1.5950157f);
   return fmaf(x * wp, fmaf(-s, s, s), s);
+}
+
+// Packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2, one issue slot for two IEEE operations) and the GELU above
+// on a pair of values: same operations in the same order as gelu_erf, hence bit-identical results, at 5.5 instead
+// of 9 issue slots per element (the GELU epilogues are issue-bound).
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t X = f2_pack(x0, x1);
+  float t0, t1;
+  f2_unpack(f2_mul(X, X), t0, t1);
+  const uint64_t T = f2_pack(fminf(t0, 25.0f), fminf(t1, 25.0f));
+  uint64_t R = f2_fma(f2_pack(0.0010142630f, 0.0010142630f), T, f2_pack(-0.10677572f, -0.10677572f));
+  R = f2_fma(R, T, f2_pack(-2.3011212f, -2.3011212f));
+  float e0, e1;
+  f2_unpack(f2_mul(X, R), e0, e1);
+  float d0, d1;
+  f2_unpack(f2_add(f2_pack(ex2_approx(e0), ex2_approx(e1)), f2_pack(1.0f, 1.0f)), d0, d1);
+  f2_unpack(f2_mul(X, f2_pack(rcp_approx(d0), rcp_approx(d1))), x0, x1);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

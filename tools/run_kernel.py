@@ -63,6 +63,20 @@ def main():
         run = lambda: L.check(L.lib().crf_mlp_fwd(Cc.byref(m), st), "crf_mlp_fwd")
         ms = timed(run, a.iters)
         byt = T * C * (8 + (0 if a.infer else 18))
+        if os.environ.get("CRF_MLP_PROF") == "1":   # debug timeline of CTA 0 (csrc/crf_mlp_fused.cu MLP_PROF)
+            EV, CH = 16, 96
+            buf = (Cc.c_longlong * (EV * CH))()
+            L.lib().crf_debug_mlp_prof.argtypes = [Cc.POINTER(Cc.c_longlong), Cc.c_int]
+            L.lib().crf_debug_mlp_prof(buf, EV * CH)
+            t = [[buf[e * CH + c] for c in range(CH)] for e in range(EV)]
+            t00 = min(v for row in t for v in row if v > 0)
+            names = ["fc1_beg", "fc1_end", "g_pre", "g_math", "g_wait", "g_arr", "fc2_act", "fc2_w2", "fc2_end", "w1_ld", "w2_ld"]
+            print("chunk " + " ".join(f"{n:>8s}" for n in names))
+            for c in range(40):
+                print(f"{c:5d} " + " ".join(f"{(t[e][c] - t00) if t[e][c] else -1:8d}" for e in range(11)))
+            print("tile   ln_beg   ln_end  fin_beg  fin_end")
+            for c in range(6):
+                print(f"{c:4d} " + " ".join(f"{(t[e][c] - t00) if t[e][c] else -1:8d}" for e in (11, 12, 13, 14)))
         print(f"mlp_fused T={T} C={C} {'infer' if a.infer else 'train'}: {ms * 1e3:.1f} us, "
               f"{16.0 * T * C * C / ms / 1e9:.1f} TFLOP/s, {byt / ms / 1e6:.0f} GB/s")
     elif a.what == "attn":
