@@ -414,14 +414,24 @@ def run_ours(args):
         return B * (-(-Hs // 7)) * (-(-Ws // 7))
 
     def block_flops(Hs, Ws, Cd):
-        return 3.0 * n_windows(Hs, Ws) * (22 * 49 * Cd * Cd + 4 * 49 * 49 * Cd)
+        # qk / attention / proj act on the padded tokens Tp = 49 * windows, LayerNorm / MLP on the real
+        # tokens T; forward = Tp * (6 C^2 + 196 C) + T * 16 C^2, x3 with backward (60.29 GFLOP forward at 120x160, C = 128,
+        # B = 8; all eight blocks of the step: 1454.6 GFLOP)
+        Tp, T_ = 49.0 * n_windows(Hs, Ws), float(B * Hs * Ws)
+        return 3.0 * (Tp * (6 * Cd * Cd + 196 * Cd) + T_ * 16 * Cd * Cd)
+
+    def block_min_bytes(Hs, Ws, Cd, nH):
+        # fully fused block, bf16 activations: per window 49 * 8 C * 2 B forward+backward (x, v -> y; x, v, dy -> dx, dv),
+        # plus the fp32 parameters read once per direction and their gradients written once
+        params = 11 * Cd * Cd + 12 * Cd + 169 * nH
+        return n_windows(Hs, Ws) * 49 * 8 * Cd * 2 + 3 * params * 4
 
     BLOCK_PREFIXES = ("gemm_", "attn_", "ln_fwd", "ln_bwd", "cast4", "cast_bf16", "convert_bf16", "mlp_fused", "splitk_reduce")
     blk_k = [k for k in kernels if k["kernel"].startswith(BLOCK_PREFIXES)]
     blk_ms = sum(k["total_ms"] for k in blk_k) / args.steps                       # per step, all eight blocks
     blk_bytes = sum(k["bytes"] * k["launches"] for k in blk_k) / args.steps       # sum of per-kernel algorithmic bytes
     step_flops = sum(2 * block_flops(H // sc, W // sc, Cd) for sc, Cd, _ in STAGES)
-    step_min_bytes = sum(2 * B * (H // sc) * (W // sc) * 8 * Cd * 2 for sc, Cd, _ in STAGES)
+    step_min_bytes = sum(2 * block_min_bytes(H // sc, W // sc, Cd, nH_) for sc, Cd, nH_ in STAGES)
     tf = step_flops / (blk_ms * 1e-3) / 1e12 if blk_ms else 0.0
     traffic, traffic_src = None, None
     try:   # DRAM bytes of the block kernels from the committed `ncu --set full` captures, where all of them were captured
@@ -491,8 +501,8 @@ def run_ours(args):
                    "ms_fwd_bwd": ms_b, "ms_fwd_bwd_eager": ms_eager, "cuda_graph": graphed,
                    "windows_per_s": nwin / (ms_b * 1e-3), "algorithmic_tflops": fl / (ms_b * 1e-3) / 1e12,
                    "frac_of_bf16_peak": fl / (ms_b * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
-                   "min_bytes_MB": B * Hs * Ws * 16 * Cd / 1e6,
-                   "frac_of_hbm_peak_on_min_bytes": B * Hs * Ws * 16 * Cd / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                   "min_bytes_MB": block_min_bytes(Hs, Ws, Cd, nH) / 1e6,
+                   "frac_of_hbm_peak_on_min_bytes": block_min_bytes(Hs, Ws, Cd, nH) / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"]}
             for k in kernels:
                 for tag in ("attn_fwd", "attn_bwd"):
                     if k["kernel"] == f"{tag}_B{B}_{Hs}x{Ws}_C{Cd}_s3" and k["total_ms"] > 0:

@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define CRF_ABI_VERSION 2
+enum { CRF_PREC_BF16 = 0, CRF_PREC_FP32 = 1 };
 
 enum { CRF_DT_F32 = 0, CRF_DT_BF16 = 1 };
 
@@ -53,6 +54,10 @@ typedef struct crf_block_desc {
   int32_t v_preconverted; /* 1: `v` already is the bf16 token-major copy produced by crf_convert_v */
   int64_t x_stride_b, x_stride_t, x_stride_c;
   int64_t v_stride_b, v_stride_h, v_stride_w, v_stride_c;
+  int32_t precision;      /* CRF_PREC_BF16 (default): bf16 tensor-core operands and intermediates, rel 2e-2;
+                           * CRF_PREC_FP32: split-operand tensor-core GEMMs + fp32 attention / intermediates, rel 1e-3
+                           * (BASELINE.json's two tolerance tiers).  v_preconverted must be 0 in the fp32 mode. */
+  int32_t reserved;
 } crf_block_desc;
 
 /* fp32 parameters of one CRFBlock, names as in the reference state_dict. */
@@ -72,6 +77,12 @@ typedef struct crf_block_params {
   const float* fc2_b;    /* (C)      */
   float qk_scale;        /* head_dim^-0.5 unless overridden (newcrf_layers.py:83) */
   float ln_eps;          /* 1e-5 */
+  const float* ext_mask; /* NULL: the shifted-window mask of BasicCRFLayer.forward (newcrf_layers.py:332-350), evaluated
+                          * in closed form.  Otherwise an additive (ext_mask_windows, 49, 49) f32 mask that REPLACES it
+                          * (CRFBlock.forward's mask_matrix argument, :195,236): window w of every image uses
+                          * ext_mask[w mod ext_mask_windows]. */
+  int32_t ext_mask_windows;
+  int32_t reserved;
 } crf_block_params;
 
 /* fp32 gradient outputs, same shapes as crf_block_params; the library ACCUMULATES (+=) into them, so the
@@ -193,6 +204,9 @@ typedef struct crf_gemm_args {
   void* workspace;         /* CRF_EPI_SPLITK_F32: fp32 partial tiles (crf_gemm_workspace_bytes) or NULL */
   size_t workspace_bytes;
   float* colsum;           /* MN-major A only: colsum[m] += sum_k A(m,k) (bias gradient fused into wgrad), or NULL */
+  int32_t split3;          /* 1: split-operand fp32 emulation.  A and B hold fp32 values as two bf16 terms side by side,
+                            * [hi | lo] (twice as many columns as the logical matrix: (M, 2K) / (K, 2M) ...), and the
+                            * product accumulates hi*hi + hi*lo + lo*hi in fp32.  fp32 epilogues only. */
 } crf_gemm_args;
 int crf_gemm(const crf_gemm_args* a, void* stream);
 /* workspace a CRF_EPI_SPLITK_F32 GEMM of this shape wants (0 when it runs as a single split) */

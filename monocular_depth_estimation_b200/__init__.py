@@ -7,5 +7,6 @@ repository adopts it.
 """
 from .newcrf_layers import BasicCRFLayer, CRFBlock, Mlp, NewCRF, WindowAttention  # noqa: F401
 from .functional import crf_block, convert_v  # noqa: F401
+from .ops import set_precision  # noqa: F401
 
-__all__ = ["BasicCRFLayer", "CRFBlock", "Mlp", "NewCRF", "WindowAttention", "crf_block", "convert_v"]
+__all__ = ["BasicCRFLayer", "CRFBlock", "Mlp", "NewCRF", "WindowAttention", "crf_block", "convert_v", "set_precision"]

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcrf_sm100.so")
 CRF_DT_F32 = 0
 CRF_DT_BF16 = 1
 
+PREC_BF16, PREC_FP32 = 0, 1   # crf_block_desc.precision (BASELINE.json: rel 2e-2 / rel 1e-3 tiers)
 EPI_STORE_F32 = 0
 EPI_STORE_BF16 = 1
 EPI_BIAS_RES_F32 = 2
@@ -44,6 +45,7 @@ class BlockDesc(C.Structure):
         ("x_dtype", C.c_int32), ("v_dtype", C.c_int32), ("v_preconverted", C.c_int32),
         ("x_stride_b", C.c_int64), ("x_stride_t", C.c_int64), ("x_stride_c", C.c_int64),
         ("v_stride_b", C.c_int64), ("v_stride_h", C.c_int64), ("v_stride_w", C.c_int64), ("v_stride_c", C.c_int64),
+        ("precision", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -52,7 +54,8 @@ PARAM_NAMES = ("norm1_w", "norm1_b", "qk_w", "qk_b", "rpb_table", "proj_w", "pro
 
 
 class BlockParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in PARAM_NAMES] + [("qk_scale", C.c_float), ("ln_eps", C.c_float)]
+    _fields_ = ([(n, C.c_void_p) for n in PARAM_NAMES] + [("qk_scale", C.c_float), ("ln_eps", C.c_float)]
+                + [("ext_mask", C.c_void_p), ("ext_mask_windows", C.c_int32), ("reserved", C.c_int32)])
 
 
 class BlockGrads(C.Structure):
@@ -77,6 +80,7 @@ class GemmArgs(C.Structure):
         ("device", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("colsum", C.c_void_p),
+        ("split3", C.c_int32),
     ]
 
 

@@ -141,9 +141,10 @@ size_t crf_timing_report(char* buf, size_t cap) { return timing_report(buf, cap)
 
 int crf_block_sizes(const crf_block_desc* d, size_t* saved_bytes, size_t* ws_fwd_bytes, size_t* ws_bwd_bytes) {
   if (check_desc(d)) return 1;
-  if (saved_bytes) *saved_bytes = saved_layout(*d).total;
+  const bool fp32 = d->precision == CRF_PREC_FP32;
+  if (saved_bytes) *saved_bytes = fp32 ? precise_saved_bytes(*d) : saved_layout(*d).total;
   if (ws_fwd_bytes) *ws_fwd_bytes = 256;  // forward needs no scratch beyond `saved`
-  if (ws_bwd_bytes) *ws_bwd_bytes = bwd_layout(*d).total;
+  if (ws_bwd_bytes) *ws_bwd_bytes = fp32 ? precise_bwd_bytes(*d) : bwd_layout(*d).total;
   return 0;
 }
 
@@ -163,9 +164,11 @@ static int block_fwd_impl(const crf_block_desc* d, const crf_block_params* p, co
                           void* saved, void* stream) {
   if (check_desc(d)) return 1;
   CRF_CHECK(p && x && v && y && saved, "crf_block_fwd: null pointer");
+  CRF_CHECK(p->ext_mask == nullptr || p->ext_mask_windows > 0, "crf_block_fwd: ext_mask needs ext_mask_windows > 0");
   DeviceGuard guard(d->device);
   CRF_CHECK(guard.ok, "cannot select device %d", d->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->precision == CRF_PREC_FP32) return block_fwd_precise(d, p, x, v, y, saved, st);
   const SavedLayout L = saved_layout(*d);
   uint8_t* S = static_cast<uint8_t*>(saved);
   const int T = d->B * d->H * d->W, C = d->C;
@@ -196,8 +199,8 @@ static int block_fwd_impl(const crf_block_desc* d, const crf_block_params* p, co
                  p->qk_scale, C, d->device, st))
     return 1;
   // window attention core
-  if (launch_attn_fwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, nullptr, 0, S + L.attn_o,
-                      d->training ? reinterpret_cast<float*>(S + L.lse) : nullptr, st))
+  if (launch_attn_fwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, p->ext_mask, p->ext_mask_windows,
+                      S + L.attn_o, d->training ? reinterpret_cast<float*>(S + L.lse) : nullptr, st, /*ext_replaces=*/1))
     return 1;
   // x1 = x + proj(attn)
   if (gemm_fprop(S + L.attn_o, S + L.wb_proj, T, C, C, CRF_EPI_BIAS_RES_F32, S + L.x1, nullptr, p->proj_b, x_tok, 1.f,
@@ -236,6 +239,12 @@ static int block_bwd_impl(const crf_block_desc* d, const crf_block_params* p, co
   if (check_desc(d)) return 1;
   CRF_CHECK(p && x && v && dy && saved && (dx || dx_bf16) && dv && g && ws, "crf_block_bwd: null pointer");
   CRF_CHECK(d->training, "crf_block_bwd: forward was not run with training=1");
+  if (d->precision == CRF_PREC_FP32) {
+    DeviceGuard guard(d->device);
+    CRF_CHECK(guard.ok, "cannot select device %d", d->device);
+    return block_bwd_precise(d, p, x, v, dy, saved, dx, dx_bf16, dv, dv_accumulate, g, ws, ws_bytes,
+                             static_cast<cudaStream_t>(stream));
+  }
   const BwdLayout W = bwd_layout(*d);
   CRF_CHECK(ws_bytes >= W.total, "crf_block_bwd: workspace too small (%zu < %zu)", ws_bytes, W.total);
   DeviceGuard guard(d->device);
@@ -267,9 +276,9 @@ static int block_bwd_impl(const crf_block_desc* d, const crf_block_params* p, co
   // ---- attention ----
   if (gemm_dgrad(Wk + W.dx1b, S + L.wb_proj, T, C, C, CRF_EPI_STORE_BF16, Wk + W.dob, nullptr, dev, st)) return 1;
   if (gemm_wgrad(Wk + W.dx1b, S + L.attn_o, C, C, T, g->proj_w, g->proj_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, nullptr, 0,
+  if (launch_attn_bwd(*d, S + L.qk, vb, p->qk_b, p->qk_scale, p->rpb_table, p->ext_mask, p->ext_mask_windows,
                       reinterpret_cast<const float*>(S + L.lse),
-                      Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st))
+                      Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st, /*ext_replaces=*/1))
     return 1;
   if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st)) return 1;
   if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, g->qk_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
@@ -303,7 +312,7 @@ struct LayerLayout {
 crf_block_desc block_desc_of(const crf_block_desc& d, int i) {
   crf_block_desc b = d;
   b.shift = (i % 2 == 0) ? 0 : d.window / 2;
-  b.v_preconverted = 1;
+  b.v_preconverted = d.precision == CRF_PREC_FP32 ? 0 : 1;  // the fp32 mode reads v as it is, with its own strides
   if (i > 0) {  // blocks after the first read the previous block's contiguous fp32 output
     b.x_dtype = CRF_DT_F32;
     b.x_stride_c = 1;
@@ -317,9 +326,10 @@ LayerLayout layer_layout(const crf_block_desc& d, int depth, int with_norm) {
   const size_t T = static_cast<size_t>(d.B) * d.H * d.W, C = d.C;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
-  L.vb = take(T * C * 2);
+  const bool fp32 = d.precision == CRF_PREC_FP32;
+  L.vb = take(fp32 ? 0 : T * C * 2);
   for (int i = 0; i < depth; ++i) {
-    L.blk[i] = take(saved_layout(block_desc_of(d, i)).total);
+    L.blk[i] = take(fp32 ? precise_saved_bytes(block_desc_of(d, i)) : saved_layout(block_desc_of(d, i)).total);
     // the last block's output is the caller's y unless a closing norm follows (then LN backward needs it)
     L.yout[i] = (i + 1 < depth || with_norm) ? take(T * C * 4) : 0;
   }
@@ -335,7 +345,8 @@ LayerBwdLayout layer_bwd_layout(const crf_block_desc& d, int depth, int with_nor
   const size_t T = static_cast<size_t>(d.B) * d.H * d.W, C = d.C;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return r; };
-  L.blk = take(bwd_layout(block_desc_of(d, depth > 1 ? 1 : 0)).total);
+  L.blk = take(d.precision == CRF_PREC_FP32 ? precise_bwd_bytes(block_desc_of(d, depth > 1 ? 1 : 0))
+                                            : bwd_layout(block_desc_of(d, depth > 1 ? 1 : 0)).total);
   L.g_f32 = take(with_norm ? T * C * 4 : 0);
   L.g_bf16 = take(with_norm ? T * C * 2 : 0);
   for (int k = 0; k < 2; ++k) {  // ping-pong buffers for the gradient between blocks (each slot aligned on its own)
@@ -374,14 +385,19 @@ int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
   const LayerLayout L = layer_layout(*d, a->depth, with_norm);
   uint8_t* S = static_cast<uint8_t*>(saved);
   const int T = d->B * d->H * d->W;
-  crf_block_desc d0 = *d;
-  d0.v_preconverted = 0;
-  if (crf_convert_v(&d0, v, S + L.vb, stream)) return 1;
+  const bool fp32 = d->precision == CRF_PREC_FP32;
+  const void* vin = v;
+  if (!fp32) {
+    crf_block_desc d0 = *d;
+    d0.v_preconverted = 0;
+    if (crf_convert_v(&d0, v, S + L.vb, stream)) return 1;
+    vin = S + L.vb;
+  }
   const void* xin = x;
   for (int i = 0; i < a->depth; ++i) {
     const crf_block_desc bd = block_desc_of(*d, i);
     float* yo = (i + 1 == a->depth && !with_norm) ? static_cast<float*>(y) : reinterpret_cast<float*>(S + L.yout[i]);
-    if (block_fwd_impl(&bd, a->params + i, xin, S + L.vb, yo, S + L.blk[i], stream)) return 1;
+    if (block_fwd_impl(&bd, a->params + i, xin, vin, yo, S + L.blk[i], stream)) return 1;
     xin = yo;
   }
   if (with_norm) {
@@ -395,9 +411,9 @@ int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
 int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, const void* dy,
                   const void* saved, void* dx, float* dv, const crf_block_grads* g, float* dnorm_w, float* dnorm_b,
                   void* ws, size_t ws_bytes, void* stream) {
-  (void)v;
   if (check_layer(d, a)) return 1;
   CRF_CHECK(x && dy && saved && dx && dv && g && ws, "crf_layer_bwd: null pointer");
+  CRF_CHECK(d->precision != CRF_PREC_FP32 || v != nullptr, "crf_layer_bwd: the fp32 mode re-reads v");
   CRF_CHECK(d->training, "crf_layer_bwd: forward was not run with training=1");
   const int with_norm = a->norm_w != nullptr;
   CRF_CHECK(!with_norm || (dnorm_w && dnorm_b), "crf_layer_bwd: gradient buffers of the closing norm are missing");
@@ -440,8 +456,10 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
                         : reinterpret_cast<float*>(Wk + W.mid_f32[i & 1]);
     void* dxo16 = i == 0 ? (dx_is_bf16 ? dx : nullptr)
                          : static_cast<void*>(Wk + W.mid_bf16[i & 1]);
-    if (block_bwd_impl(&bd, a->params + i, xin, S + L.vb, g32, g16, S + L.blk[i], dxo, dxo16, dv,
-                       i == a->depth - 1 ? 0 : 1, g + i, Wk + W.blk, bwd_layout(bd).total, stream))
+    const bool fp32 = d->precision == CRF_PREC_FP32;
+    if (block_bwd_impl(&bd, a->params + i, xin, fp32 ? v : static_cast<const void*>(S + L.vb), g32, g16, S + L.blk[i], dxo,
+                       dxo16, dv, i == a->depth - 1 ? 0 : 1, g + i, Wk + W.blk,
+                       fp32 ? precise_bwd_bytes(bd) : bwd_layout(bd).total, stream))
       return 1;
     g32 = dxo;
     g16 = dxo16;

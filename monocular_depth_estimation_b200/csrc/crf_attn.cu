@@ -35,7 +35,8 @@ int fill_attn_params(AttnParams& P, const crf_block_desc& d) {
 }
 
 int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                    const float* table, const float* ext_mask, int ext_mask_nw, void* o, float* lse, cudaStream_t st) {
+                    const float* table, const float* ext_mask, int ext_mask_nw, void* o, float* lse, cudaStream_t st,
+                    int ext_replaces) {
   AttnParams P{};
   if (fill_attn_params(P, d)) return 1;
   P.qk = reinterpret_cast<const __nv_bfloat16*>(qk);
@@ -45,6 +46,7 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.scale = scale;
   P.ext_mask = ext_mask_nw > 0 ? ext_mask : nullptr;
   P.ext_mask_nw = ext_mask_nw > 0 ? ext_mask_nw : 1;
+  P.ext_replaces = (P.ext_mask != nullptr && ext_replaces) ? 1 : 0;
   P.o = reinterpret_cast<__nv_bfloat16*>(o);
   P.lse = lse;
   return P.hd > 32 ? launch_attn_fwd_wide(P, d, st) : launch_attn_fwd_async(P, d, st);
@@ -52,7 +54,7 @@ int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, con
 
 int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
                     const float* table, const float* ext_mask, int ext_mask_nw, const float* lse, const void* dout,
-                    void* dqk, float* dv, int dv_acc, float* d_table, float* d_qk_bias, cudaStream_t st) {
+                    void* dqk, float* dv, int dv_acc, float* d_table, float* d_qk_bias, cudaStream_t st, int ext_replaces) {
   AttnParams P{};
   if (fill_attn_params(P, d)) return 1;
   P.qk = reinterpret_cast<const __nv_bfloat16*>(qk);
@@ -62,6 +64,7 @@ int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, con
   P.scale = scale;
   P.ext_mask = ext_mask_nw > 0 ? ext_mask : nullptr;
   P.ext_mask_nw = ext_mask_nw > 0 ? ext_mask_nw : 1;
+  P.ext_replaces = (P.ext_mask != nullptr && ext_replaces) ? 1 : 0;
   P.lse = const_cast<float*>(lse);
   P.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   P.dqk = reinterpret_cast<__nv_bfloat16*>(dqk);

@@ -149,6 +149,7 @@ __device__ __forceinline__ RowView row_view(const AttnParams& P, int pair, int h
     if (w.hsplit) m |= (pi >= lo) ? ~far_h : far_h;
     if (w.wsplit) m |= (pj >= lo) ? ~far_w : far_w;
     m &= (1ull << kNTok) - 1;
+    if (P.ext_replaces) m = 0;
     v.m_lo = static_cast<uint32_t>(m);
     v.m_hi = static_cast<uint32_t>(m >> 32);
   }

@@ -22,6 +22,7 @@ struct AttnParams {
   float scale;
   const float* ext_mask;     // optional additive mask (nwm, 49, 49) f32, window index = global window % nwm; or nullptr
   int ext_mask_nw;
+  int ext_replaces;          // 1: ext_mask REPLACES the closed-form shift mask (CRFBlock.forward's mask_matrix); 0: added on top
   // forward
   __nv_bfloat16* o;          // (T, C)
   float* lse;                // (B*nW, nH, 64)

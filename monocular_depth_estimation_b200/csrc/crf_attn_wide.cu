@@ -179,7 +179,7 @@ attn_fwd_wide_kernel(const AttnParams P) {
         const int bi = rpb_base(pos);
         const uint8_t* rrow = rid + half * 64;
         const int my_region = rrow[pos];
-        const bool masked = P.gm.shift > 0;
+        const bool masked = P.gm.shift > 0 && !P.ext_replaces;
         const float* xmask = P.ext_mask != nullptr
                                  ? P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok
                                  : nullptr;
@@ -402,7 +402,7 @@ attn_bwd_wide_kernel(const AttnParams P) {
           const int bi = rpb_base(pos);
           const uint8_t* rrow = rid + half * 64;
           const int my_region = rrow[pos];
-          const bool masked = P.gm.shift > 0;
+          const bool masked = P.gm.shift > 0 && !P.ext_replaces;
           const float* xmask = P.ext_mask != nullptr
                                    ? P.ext_mask + (static_cast<int64_t>(wg % P.ext_mask_nw) * kNTok + pos) * kNTok
                                    : nullptr;

@@ -43,12 +43,19 @@ __global__ void __launch_bounds__(kThreads)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
             const __grid_constant__ CUtensorMap tmAux, int M, int N, int total_chunks, int chunks_per_split, int stages,
-            int a_major, int b_major, EpiParams ep) {
+            int a_major, int b_major, EpiParams ep, int chunks_per_part, int a_off, int b_off) {
+  // chunks_per_part > 0: split-operand mode (crf_gemm_args.split3).  Both operands are stored as [hi | lo] halves side
+  // by side and the K loop runs three times: chunk kc belongs to part kc / chunks_per_part = 0: hi*hi, 1: hi*lo(B),
+  // 2: lo(A)*hi; the lo half of an operand is a_off / b_off elements further along its contiguous dimension.
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = kATileBytes + kBTileBytes;
   // Bias gradient for free: one extra N=16 MMA per K step against an all-ones B tile puts sum_k A(m,k) into 16
   // spare TMEM columns (every column holds the same sum); needs the next power of two of TMEM columns.
-  const bool do_colsum = ep.colsum != nullptr && blockIdx.y == 0;
+  const int kc_begin_ = blockIdx.z * chunks_per_split;
+  const int kc_end_ = min(total_chunks, kc_begin_ + chunks_per_split);
+  // split-operand mode: the column sums of A = hi + lo come from parts 0 (hi) and 2 (lo) only
+  const bool cs_any = chunks_per_part == 0 || kc_begin_ < chunks_per_part || kc_end_ > 2 * chunks_per_part;
+  const bool do_colsum = ep.colsum != nullptr && blockIdx.y == 0 && cs_any;
   const uint32_t kTmemCols = ep.colsum != nullptr ? 2u * BN : (BN < 32 ? 32u : static_cast<uint32_t>(BN));
   constexpr bool kOutF32 = (EPI == CRF_EPI_STORE_F32 || EPI == CRF_EPI_BIAS_RES_F32 || EPI == CRF_EPI_SPLITK_F32);
   constexpr bool kHasAux = (EPI == CRF_EPI_BIAS_RES_F32 || EPI == CRF_EPI_MUL_DGELU);
@@ -119,18 +126,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t a_dst = smem_base + s * kStageBytes;
         const uint32_t b_dst = a_dst + kATileBytes;
         mbar_expect_tx(full_bar(s), kStageBytes);
-        const int k0 = (kc_begin + i) * BK;
+        const int kc = kc_begin + i;
+        const int part = chunks_per_part ? kc / chunks_per_part : 0;
+        const int k0 = (kc - part * chunks_per_part) * BK;
+        const int ao = part == 2 ? a_off : 0, bo = part == 1 ? b_off : 0;
         if (a_major == 0) {
-          tma_load_2d(a_dst, &tmA, full_bar(s), k0, m0);
+          tma_load_2d(a_dst, &tmA, full_bar(s), k0 + ao, m0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, full_bar(s), m0 + 64 * j, k0);
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, full_bar(s), m0 + 64 * j + ao, k0);
         }
         if (b_major == 0) {
-          tma_load_2d(b_dst, &tmB, full_bar(s), k0, n0);
+          tma_load_2d(b_dst, &tmB, full_bar(s), k0 + bo, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, full_bar(s), n0 + 64 * j, k0);
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, full_bar(s), n0 + 64 * j + bo, k0);
         }
       }
     }
@@ -138,7 +148,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(1u, static_cast<uint32_t>(a_major), static_cast<uint32_t>(b_major), BM, BN);
+      uint32_t cs_acc = 0u;
       for (int i = 0; i < nk; ++i) {
+        const bool cs_part = chunks_per_part == 0 || (kc_begin + i) / chunks_per_part != 1;
         const int s = i % stages;
         mbar_wait(full_bar(s), (i / stages) & 1);
         tc_fence_after();
@@ -151,9 +163,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bd = (b_major == 0) ? make_smem_desc(b_src + ks * 32, 16, 1024, kSwizzle128)
                                              : make_smem_desc(b_src + ks * 2048, 8192, 1024, kSwizzle128);
           umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-          if (do_colsum)  // K-major, no swizzle: 8x16-byte core matrices, 128 B apart along K, 256 B along N
+          if (do_colsum && cs_part) {  // K-major, no swizzle: 8x16-byte core matrices, 128 B apart along K, 256 B along N
             umma_bf16(tmem_base + BN, ad, make_smem_desc(ones_addr, 128, 256, kSwizzleNone),
-                      make_idesc(1u, static_cast<uint32_t>(a_major), 0u, BM, 16), (i > 0 || ks > 0) ? 1u : 0u);
+                      make_idesc(1u, static_cast<uint32_t>(a_major), 0u, BM, 16), cs_acc);
+            cs_acc = 1u;
+          }
         }
         umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
       }
@@ -246,6 +260,7 @@ struct Launch {
   CUtensorMap tmA, tmB, tmO0, tmO1, tmAux;
   int total_chunks, cps, splits, m_pad;
   int tma_reduce = 0;
+  int chunks_per_part = 0, a_off = 0, b_off = 0;  // split-operand mode
 };
 
 template <int BN, int EPI>
@@ -271,10 +286,11 @@ int launch_one(const Launch& L, const crf_gemm_args& a, cudaStream_t st) {
                            : EPI == CRF_EPI_BIAS_RES_F32 ? 8 * mn
                            : EPI == CRF_EPI_BIAS_GELU ? (a.out0 != nullptr ? 4 * mn : 2 * mn)
                            : 4 * mn;
-  KernelTimer tm(st, 2.0 * mn * a.K, 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
-                 "gemm_%s_epi%d_M%d_N%d_K%d", a.a_major ? "wgrad" : (a.b_major ? "dgrad" : "fprop"), EPI, a.M, a.N, a.K);
+  KernelTimer tm(st, 2.0 * mn * a.K, (a.split3 ? 2.0 : 1.0) * 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
+                 "gemm%s_%s_epi%d_M%d_N%d_K%d", a.split3 ? "3" : "", a.a_major ? "wgrad" : (a.b_major ? "dgrad" : "fprop"), EPI,
+                 a.M, a.N, a.K);
   kern<<<grid, kThreads, smem, st>>>(L.tmA, L.tmB, L.tmO0, L.tmO1, L.tmAux, a.M, a.N, L.total_chunks, L.cps, stages,
-                                     a.a_major, a.b_major, ep);
+                                     a.a_major, a.b_major, ep, L.chunks_per_part, L.a_off, L.b_off);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;
@@ -327,7 +343,7 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   CRF_CHECK(a.ld_out == a.N, "crf_gemm: outputs must be dense (ld_out == N)");
   {  // token-major projections with N % 128 == 0 run on the persistent kernel (crf_gemm_persist.cu)
     static const bool persist = !(getenv("CRF_GEMM_PERSIST") && atoi(getenv("CRF_GEMM_PERSIST")) == 0);
-    if (persist) {
+    if (persist && !a.split3) {
       const int rc = launch_gemm_persistent(a, st);
       if (rc >= 0) return rc;
     }
@@ -340,17 +356,31 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   }
 
   Launch L{};
+  const int dup = a.split3 ? 2 : 1;  // split-operand matrices are twice as wide: [hi | lo]
+  if (a.split3) {
+    CRF_CHECK((a.a_major == 1 || a.K % BK == 0) && (a.b_major == 1 || a.K % BK == 0),
+              "crf_gemm: split3 with a K-major operand needs K %% 64 == 0 (K=%d)", a.K);
+    CRF_CHECK((a.a_major == 0 || a.M % 64 == 0), "crf_gemm: split3 with MN-major A needs M %% 64 == 0 (M=%d)", a.M);
+    CRF_CHECK(a.epilogue == CRF_EPI_STORE_F32 || a.epilogue == CRF_EPI_BIAS_RES_F32 || a.epilogue == CRF_EPI_SPLITK_F32,
+              "crf_gemm: split3 supports the fp32 epilogues only");
+  }
   if (a.a_major == 0) {
-    if (make_tmap_bf16(&L.tmA, a.A, a.M, a.K, BM)) return 1;
+    if (make_tmap_bf16(&L.tmA, a.A, a.M, static_cast<uint64_t>(dup) * a.K, BM)) return 1;
   } else {
-    if (make_tmap_bf16(&L.tmA, a.A, a.K, a.M, 64)) return 1;
+    if (make_tmap_bf16(&L.tmA, a.A, a.K, static_cast<uint64_t>(dup) * a.M, 64)) return 1;
   }
   if (a.b_major == 0) {
-    if (make_tmap_bf16(&L.tmB, a.B, a.N, a.K, BN)) return 1;
+    if (make_tmap_bf16(&L.tmB, a.B, a.N, static_cast<uint64_t>(dup) * a.K, BN)) return 1;
   } else {
-    if (make_tmap_bf16(&L.tmB, a.B, a.K, a.N, 64)) return 1;
+    if (make_tmap_bf16(&L.tmB, a.B, a.K, static_cast<uint64_t>(dup) * a.N, 64)) return 1;
   }
   L.total_chunks = (a.K + BK - 1) / BK;
+  if (a.split3) {
+    L.chunks_per_part = L.total_chunks;
+    L.total_chunks *= 3;
+    L.a_off = a.a_major == 0 ? a.K : a.M;
+    L.b_off = a.b_major == 0 ? a.K : a.N;
+  }
   L.splits = 1;
   L.cps = L.total_chunks;
   L.m_pad = (a.M + BM - 1) / BM * BM;
@@ -362,7 +392,7 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
     // out0 (M,N) f32 += A^T B.  One split: in-place accumulate (residual = out0).  Otherwise partials + reduce.
     CRF_CHECK(a.out0 != nullptr, "crf_gemm: out0 is null");
     int splits = 1;
-    gemm_splitk_workspace_bytes(a.M, a.N, a.K, a.device, &splits);
+    gemm_splitk_workspace_bytes(a.M, a.N, a.split3 ? 3 * a.K : a.K, a.device, &splits);
     if (a.split_k > 0 && a.split_k < splits) splits = a.split_k;
     const size_t per_split = static_cast<size_t>(L.m_pad) * a.N * sizeof(float);
     static const bool deterministic = getenv("CRF_WGRAD_DETERMINISTIC") != nullptr && atoi(getenv("CRF_WGRAD_DETERMINISTIC")) != 0;

@@ -71,6 +71,14 @@ long long launch_count();
 // ---- internal launchers (stream-ordered, no allocation) ----
 int launch_gemm(const crf_gemm_args& a, cudaStream_t st);
 int launch_gemm_persistent(const crf_gemm_args& a, cudaStream_t st);  // -1: shape not eligible
+// crf_precise.cu: the fp32 precision mode (crf_block_desc.precision == CRF_PREC_FP32)
+size_t precise_saved_bytes(const crf_block_desc& d);
+size_t precise_bwd_bytes(const crf_block_desc& d);
+int block_fwd_precise(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, float* y, void* saved,
+                      cudaStream_t st);
+int block_bwd_precise(const crf_block_desc* d, const crf_block_params* p, const void* x, const void* v, const float* dy,
+                      const void* saved, float* dx, void* dx_bf16, float* dv, int dv_accumulate, const crf_block_grads* g,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
 bool mlp_fused_supported(int C);                                      // crf_mlp_fused.cu: C = 128, 256
 int launch_mlp_fused_fwd(const crf_mlp_args& m, cudaStream_t st);
 int mlp_debug_prof(long long* out, int n);                            // CRF_MLP_PROF=1 timeline (debug)
@@ -103,9 +111,11 @@ int launch_window_scatter(const float* windows, float* x, int B, int H, int W, i
                           cudaStream_t st);
 int launch_shift_mask(float* mask, int H, int W, int window, int shift, cudaStream_t st);
 int launch_attn_fwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
-                    const float* table, const float* ext_mask, int ext_mask_nw, void* o, float* lse, cudaStream_t st);
+                    const float* table, const float* ext_mask, int ext_mask_nw, void* o, float* lse, cudaStream_t st,
+                    int ext_replaces = 0);
 int launch_attn_bwd(const crf_block_desc& d, const void* qk, const void* vb, const float* qk_bias, float scale,
                     const float* table, const float* ext_mask, int ext_mask_nw, const float* lse, const void* dout,
-                    void* dqk, float* dv, int dv_acc, float* d_table, float* d_qk_bias, cudaStream_t st);
+                    void* dqk, float* dv, int dv_acc, float* d_table, float* d_qk_bias, cudaStream_t st,
+                    int ext_replaces = 0);
 
 }  // namespace crf

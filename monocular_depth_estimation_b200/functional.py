@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .ops import make_desc
+from .ops import _precision_code, make_desc
 
 # order of the parameter tensors in every call (matches _lib.PARAM_NAMES / crf_block_params)
 PARAM_KEYS = ("norm1.weight", "norm1.bias", "attn.qk.weight", "attn.qk.bias", "attn.relative_position_bias_table",
@@ -48,12 +48,14 @@ def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _param_struct(params, qk_scale, eps):
+def _param_struct(params, qk_scale, eps, mask=None):
     ps = L.BlockParams()
     for name, t in zip(L.PARAM_NAMES, params):
         setattr(ps, name, t.data_ptr())
     ps.qk_scale = float(qk_scale)
     ps.ln_eps = float(eps)
+    if mask is not None:     # a non-standard mask_matrix: replaces the closed-form shift mask inside the kernels
+        ps.ext_mask, ps.ext_mask_windows = mask.data_ptr(), mask.shape[0]
     return ps
 
 
@@ -71,30 +73,32 @@ def convert_v(v: torch.Tensor) -> torch.Tensor:
 
 class _CRFBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, v, vb, H, W, num_heads, window, shift, qk_scale, eps, *params):
+    def forward(ctx, x, v, vb, mask, precision, H, W, num_heads, window, shift, qk_scale, eps, *params):
         B, Ltok, Cd = x.shape
         dev = x.device
         params = tuple(p.detach().contiguous() for p in params)
         training = any(ctx.needs_input_grad)  # all False under torch.no_grad()
         xd = x.detach()
-        if vb is not None:
+        if vb is not None and precision == L.PREC_BF16:
             v_arg, desc = vb, make_desc(B, H, W, Cd, num_heads, shift, window=window, training=training,
-                                        device=dev.index, x=xd, v_preconverted=1)
+                                        device=dev.index, x=xd, v_preconverted=1, precision=precision)
         else:
             v_arg = v.detach()
             if v_arg.stride(1) != W * v_arg.stride(2):
                 v_arg = v_arg.contiguous()
             desc = make_desc(B, H, W, Cd, num_heads, shift, window=window, training=training, device=dev.index,
-                             x=xd, v=v_arg)
+                             x=xd, v=v_arg, precision=precision)
+        mask = None if mask is None else mask.detach().float().contiguous()
         saved_bytes, _, ws_bwd = _sizes(desc)
         saved = _alloc_bytes(saved_bytes, dev)
         y = torch.empty(B, Ltok, Cd, dtype=torch.float32, device=dev)
-        ps = _param_struct(params, qk_scale, eps)
+        ps = _param_struct(params, qk_scale, eps, mask)
         L.check(L.lib().crf_block_fwd(C.byref(desc), C.byref(ps), xd.data_ptr(), v_arg.data_ptr(), y.data_ptr(),
                                       saved.data_ptr(), None, 0, _stream_ptr(dev)), "crf_block_fwd")
         _check_guard(saved, saved_bytes, "crf_block_fwd saved")
         if training:
             ctx.save_for_backward(xd, v_arg, saved, *params)
+            ctx.mask = mask
             ctx.desc = desc
             ctx.scalars = (qk_scale, eps, ws_bwd, H, W)
         return y
@@ -120,19 +124,22 @@ class _CRFBlockFn(torch.autograd.Function):
         gs = L.BlockGrads()
         for name, t in zip(L.PARAM_NAMES, grads):
             setattr(gs, name, t.data_ptr())
-        ps = _param_struct(params, qk_scale, eps)
+        ps = _param_struct(params, qk_scale, eps, ctx.mask)
         L.check(L.lib().crf_block_bwd(C.byref(desc), C.byref(ps), xd.data_ptr(), v_arg.data_ptr(), dy.data_ptr(),
                                       saved.data_ptr(), dx.data_ptr(), dv.data_ptr(), 0, C.byref(gs), ws.data_ptr(),
                                       ws_bwd, _stream_ptr(dev)), "crf_block_bwd")
         _check_guard(ws, ws_bwd, "crf_block_bwd workspace")
-        return (dx, dv, None, None, None, None, None, None, None, None, *grads)
+        return (dx, dv, None, None, None, None, None, None, None, None, None, None, *grads)
 
 
-def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None, eps=1e-5, v_bf16=None):
+def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None, eps=1e-5, v_bf16=None, mask=None,
+              precision=None):
     """One CRF block: LN1 -> (shifted-)window attention with q,k from x and v used raw -> +x -> LN2 -> MLP -> +.
 
     x: (B, H*W, C) fp32/bf16, any strides (the reference hands over a view of NCHW); v: (B, H, W, C);
-    params: 13 fp32 tensors in PARAM_KEYS order; v_bf16: optional result of convert_v(v) shared between blocks.
+    params: 13 fp32 tensors in PARAM_KEYS order; v_bf16: optional result of convert_v(v) shared between blocks;
+    mask: None = the shifted-window mask of BasicCRFLayer.forward in closed form, else an additive (nW, 49, 49) mask that
+    replaces it; precision: "bf16" | "fp32" | None (process default, ops.set_precision).
     Returns (B, H*W, C) fp32.  Mirrors the reference's error behaviour (newcrf_layers.py:205,143,180).
     """
     assert x.dim() == 3 and v.dim() == 4
@@ -148,7 +155,8 @@ def crf_block(x, v, H, W, params, num_heads, *, window=7, shift=0, qk_scale=None
         v = v.float()
     if qk_scale is None:
         qk_scale = (Cd // num_heads) ** -0.5
-    return _CRFBlockFn.apply(x, v, v_bf16, H, W, num_heads, window, shift, float(qk_scale), float(eps), *params)
+    return _CRFBlockFn.apply(x, v, v_bf16, mask, _precision_code(precision), H, W, num_heads, window, shift,
+                             float(qk_scale), float(eps), *params)
 
 
 class _CRFLayerFn(torch.autograd.Function):
@@ -157,7 +165,7 @@ class _CRFLayerFn(torch.autograd.Function):
     (crf_layer_fwd / crf_layer_bwd)."""
 
     @staticmethod
-    def forward(ctx, x, v, H, W, num_heads, window, qk_scale, eps, out_bf16, depth, norm_w, norm_b, *params):
+    def forward(ctx, x, v, precision, H, W, num_heads, window, qk_scale, eps, out_bf16, depth, norm_w, norm_b, *params):
         B, Ltok, Cd = x.shape
         dev = x.device
         params = tuple(p.detach().contiguous() for p in params)
@@ -167,7 +175,8 @@ class _CRFLayerFn(torch.autograd.Function):
         xd, v_arg = x.detach(), v.detach()
         if v_arg.stride(1) != W * v_arg.stride(2):
             v_arg = v_arg.contiguous()
-        desc = make_desc(B, H, W, Cd, num_heads, 0, window=window, training=training, device=dev.index, x=xd, v=v_arg)
+        desc = make_desc(B, H, W, Cd, num_heads, 0, window=window, training=training, device=dev.index, x=xd, v=v_arg,
+                         precision=precision)
         sb, wb = C.c_size_t(), C.c_size_t()
         L.check(L.lib().crf_layer_sizes(C.byref(desc), depth, int(with_norm), C.byref(sb), C.byref(wb)),
                 "crf_layer_sizes")
@@ -226,10 +235,11 @@ class _CRFLayerFn(torch.autograd.Function):
                                       ws_bytes, _stream_ptr(dev)), "crf_layer_bwd")
         _check_guard(ws, ws_bytes, "crf_layer_bwd workspace")
         gn = (views[13 * depth], views[13 * depth + 1]) if with_norm else (None, None)
-        return (dx, dv, None, None, None, None, None, None, None, None, gn[0], gn[1], *views[:13 * depth])
+        return (dx, dv, None, None, None, None, None, None, None, None, None, gn[0], gn[1], *views[:13 * depth])
 
 
-def crf_layer(x, v, H, W, block_params, num_heads, *, window=7, qk_scale=None, eps=1e-5, norm=None, out_dtype=None):
+def crf_layer(x, v, H, W, block_params, num_heads, *, window=7, qk_scale=None, eps=1e-5, norm=None, out_dtype=None,
+              precision=None):
     """BasicCRFLayer.forward as one call: block_params = [13 tensors in PARAM_KEYS order] per block (shift 0,
     window // 2, 0, ...); norm = (weight, bias) of a closing LayerNorm or None; out_dtype torch.bfloat16 only with
     norm.  Returns (B, H*W, C).  Mirrors the reference's error behaviour (newcrf_layers.py:205,143)."""
@@ -249,8 +259,8 @@ def crf_layer(x, v, H, W, block_params, num_heads, *, window=7, qk_scale=None, e
     nw, nb = norm if norm is not None else (None, None)
     out_bf16 = out_dtype == torch.bfloat16
     assert not out_bf16 or norm is not None, "bf16 output needs the closing LayerNorm"
-    return _CRFLayerFn.apply(x, v, H, W, num_heads, window, float(qk_scale), float(eps), out_bf16, len(block_params),
-                             nw, nb, *flat)
+    return _CRFLayerFn.apply(x, v, _precision_code(precision), H, W, num_heads, window, float(qk_scale), float(eps),
+                             out_bf16, len(block_params), nw, nb, *flat)
 
 
 class _LayerNormFn(torch.autograd.Function):

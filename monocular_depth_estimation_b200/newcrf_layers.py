@@ -107,6 +107,8 @@ class CRFBlock(nn.Module):
         self.mlp = Mlp(in_features=v_dim, hidden_features=int(v_dim * mlp_ratio), act_layer=act_layer, drop=drop)
         self.H = None
         self.W = None
+        self.precision = None      # None: process default (ops.set_precision); "bf16" | "fp32"
+        self._mask_checked = None  # (id, version, device) of the last mask_matrix found equal to the closed form
 
     def fused_params(self):
         """The 13 parameter tensors in the order the C ABI expects (functional.PARAM_KEYS)."""
@@ -115,21 +117,38 @@ class CRFBlock(nn.Module):
                 self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
                 self.mlp.fc2.weight, self.mlp.fc2.bias)
 
+    def _custom_mask(self, mask_matrix, H, W):
+        """None when `mask_matrix` is the mask BasicCRFLayer.forward builds for this (H, W) (newcrf_layers.py:332-350:
+        the kernels evaluate that one in closed form), else the mask itself (handed to the kernels, where it replaces
+        the closed form).  As in the reference (:225-236) an unshifted block ignores the argument."""
+        if mask_matrix is None or self.shift_size == 0:
+            return None
+        ws = self.window_size
+        hp, wp, n = -(-H // ws) * ws, -(-W // ws) * ws, ws * ws
+        assert tuple(mask_matrix.shape) == ((hp // ws) * (wp // ws), n, n), \
+            "mask_matrix does not belong to this (H, W, window_size)"
+        if not mask_matrix.is_cuda or torch.cuda.is_current_stream_capturing():
+            return mask_matrix.to(self.norm1.weight.device)   # no host comparison inside a graph capture
+        key = (id(mask_matrix), mask_matrix._version, H, W)
+        if self._mask_checked == key:
+            return None
+        from . import ops
+        if torch.equal(mask_matrix.float(), ops.shift_mask(H, W, ws, self.shift_size, mask_matrix.device)):
+            self._mask_checked = key
+            return None
+        return mask_matrix
+
     def forward(self, x, v, mask_matrix=None, v_bf16=None):
         """x: (B, H*W, C); v: (B, H, W, C); self.H / self.W set by the caller (as BasicCRFLayer does).
-        `mask_matrix` is accepted for signature compatibility: the shifted-window mask is a pure function of
-        (H, W, window, shift) and is evaluated inside the kernel."""
+        mask_matrix: the (nW, 49, 49) additive mask of a shifted block.  The standard one (what BasicCRFLayer.forward
+        builds) is recognised and evaluated in closed form inside the kernels; any other mask is honoured as given."""
         H, W = self.H, self.W
         B, Ltok, _ = x.shape
         assert Ltok == H * W, "input feature has wrong size"
-        if mask_matrix is not None and self.shift_size > 0:
-            hp = -(-H // self.window_size) * self.window_size
-            wp = -(-W // self.window_size) * self.window_size
-            n = self.window_size ** 2
-            assert tuple(mask_matrix.shape) == ((hp // self.window_size) * (wp // self.window_size), n, n), \
-                "mask_matrix does not belong to this (H, W, window_size)"
+        mask = self._custom_mask(mask_matrix, H, W)
         return CF.crf_block(x, v, H, W, self.fused_params(), self.num_heads, window=self.window_size,
-                            shift=self.shift_size, qk_scale=self.attn.scale, eps=self.norm1.eps, v_bf16=v_bf16)
+                            shift=self.shift_size, qk_scale=self.attn.scale, eps=self.norm1.eps, v_bf16=v_bf16,
+                            mask=mask, precision=self.precision)
 
 
 class BasicCRFLayer(nn.Module):
@@ -142,6 +161,7 @@ class BasicCRFLayer(nn.Module):
         self.shift_size = window_size // 2
         self.depth = depth
         self.use_checkpoint = use_checkpoint  # the fused backward recomputes S/P itself; flag kept for the signature
+        self.precision = None                 # None: process default (ops.set_precision); "bf16" | "fp32"
         self.blocks = nn.ModuleList([
             CRFBlock(dim=dim, num_heads=num_heads, v_dim=v_dim, window_size=window_size,
                      shift_size=0 if i % 2 == 0 else window_size // 2, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
@@ -168,9 +188,12 @@ class BasicCRFLayer(nn.Module):
             assert x.shape[1] == H * W, "input feature has wrong size"
             return CF.crf_layer(x, v, H, W, [b.fused_params() for b in self.blocks], blk0.num_heads,
                                 window=self.window_size, qk_scale=blk0.attn.scale, eps=blk0.norm1.eps,
-                                norm=None if norm is None else (norm.weight, norm.bias), out_dtype=out_dtype)
+                                norm=None if norm is None else (norm.weight, norm.bias), out_dtype=out_dtype,
+                                precision=self.precision)
         v_bf16 = CF.convert_v(v) if (v.is_cuda and self.depth > 1) else None  # both blocks read the same v
         for blk in self.blocks:
+            if blk.precision is None:
+                blk.precision = self.precision
             x = blk(x, v, None, v_bf16=v_bf16)
         if norm is not None:
             x = norm(x)

@@ -24,9 +24,32 @@ def _dev(t):
     return t.device.index if t.device.index is not None else torch.cuda.current_device()
 
 
+_DEFAULT_PRECISION = [L.PREC_BF16]
+
+
+def set_precision(mode):
+    """Process-wide default arithmetic of the CRF blocks: "bf16" (bf16 tensor-core operands and intermediates, the rel 2e-2
+    tier of BASELINE.json) or "fp32" (split-operand tensor-core GEMMs with fp32 intermediates and fp32 attention: the
+    rel 1e-3 tier).  Returns the previous mode.  Modules / functional calls can override it per call (precision=...)."""
+    prev = "fp32" if _DEFAULT_PRECISION[0] == L.PREC_FP32 else "bf16"
+    _DEFAULT_PRECISION[0] = _precision_code(mode)
+    return prev
+
+
+def _precision_code(mode):
+    if mode is None:
+        return _DEFAULT_PRECISION[0]
+    if mode in (L.PREC_BF16, "bf16", "bfloat16"):
+        return L.PREC_BF16
+    if mode in (L.PREC_FP32, "fp32", "float32"):
+        return L.PREC_FP32
+    raise ValueError(f"precision must be 'bf16' or 'fp32' (got {mode!r})")
+
+
 def make_desc(B, H, W, Cdim, num_heads, shift, *, window=7, training=1, device=0, x=None, v=None,
-              v_preconverted=0):
+              v_preconverted=0, precision=None):
     d = L.BlockDesc()
+    d.precision = _precision_code(precision)
     d.B, d.H, d.W, d.C = B, H, W, Cdim
     d.num_heads, d.window, d.shift = num_heads, window, shift
     d.training, d.device = int(training), int(device)

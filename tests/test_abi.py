@@ -46,9 +46,9 @@ def test_version_and_error_reporting_without_gpu():
 
 
 def test_struct_sizes_match_header_layout():
-    # 12 int32 + 7 int64 ; 13 pointers + 2 floats ; 13 pointers
-    assert ctypes.sizeof(_lib.BlockDesc) == 12 * 4 + 7 * 8
-    assert ctypes.sizeof(_lib.BlockParams) == 13 * 8 + 8
+    # 12 int32 + 7 int64 + 2 int32 ; 13 pointers + 2 floats + pointer + 2 int32 ; 13 pointers
+    assert ctypes.sizeof(_lib.BlockDesc) == 12 * 4 + 7 * 8 + 8
+    assert ctypes.sizeof(_lib.BlockParams) == 13 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.BlockGrads) == 13 * 8
 
 
@@ -61,7 +61,7 @@ def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
         pytest.skip("gcc not available")
     structs = {"crf_block_desc": _lib.BlockDesc, "crf_block_params": _lib.BlockParams,
                "crf_block_grads": _lib.BlockGrads, "crf_layer_args": _lib.LayerArgs, "crf_gemm_args": _lib.GemmArgs,
-               "crf_adam_tensor": _lib.AdamTensor}
+               "crf_adam_tensor": _lib.AdamTensor, "crf_mlp_args": _lib.MlpArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "crf_sm100.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -146,7 +146,7 @@ def test_layer_call_bf16_inputs_gradient_dtype():
     assert rel_l2(outs[0][2].float(), outs[1][2].float()) < 1e-2
 
 
-def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device):
+def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device, precision=None, tol=TOL, mask=None):
     from monocular_depth_estimation_b200 import functional as CF
     gen = torch.Generator().manual_seed(seed)
     p = O.init_block_params(C, nH, gen)
@@ -161,7 +161,7 @@ def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device):
     po = {k: t.detach().clone().to(oracle_device).requires_grad_(True) for k, t in p.items()}
     xo = x.to(oracle_device).detach().requires_grad_(True)
     vo = v.to(oracle_device).detach().requires_grad_(True)
-    yo = O.crf_block(xo, vo, H, W, po, nH, 7, shift)
+    yo = O.crf_block(xo, vo, H, W, po, nH, 7, shift, mask_matrix=mask)
     yo.backward(dy.to(oracle_device))
     # CUDA path
     pc = {k: t.detach().clone().to(DEV).requires_grad_(True) for k, t in p.items()}
@@ -171,16 +171,96 @@ def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device):
         assert not xc.is_contiguous()
     xc = xc.detach().requires_grad_(True)
     vc = vc.detach().requires_grad_(True)
-    yc = CF.crf_block(xc, vc, H, W, [pc[k] for k in CF.PARAM_KEYS], nH, window=7, shift=shift)
+    yc = CF.crf_block(xc, vc, H, W, [pc[k] for k in CF.PARAM_KEYS], nH, window=7, shift=shift, precision=precision,
+                      mask=None if mask is None else mask.to(DEV))
     yc.backward(dy.to(DEV))
     torch.cuda.synchronize()
     errs = {"y": rel_l2(yc.detach(), yo.detach()), "dx": rel_l2(xc.grad, xo.grad), "dv": rel_l2(vc.grad, vo.grad)}
     for k in CF.PARAM_KEYS:
         errs[k] = rel_l2(pc[k].grad, po[k].grad)
-    _report(f"block B{B} {H}x{W} C{C} nH{nH} shift{shift} strided{int(strided)} oracle@{oracle_device}", errs)
-    bad = {k: e for k, e in errs.items() if not e < TOL}
-    assert not bad, f"rel_l2 above {TOL}: {bad}\nall: {errs}"
+    _report(f"block B{B} {H}x{W} C{C} nH{nH} shift{shift} strided{int(strided)} oracle@{oracle_device}"
+            + (f" precision={precision}" if precision else "") + (" custom-mask" if mask is not None else ""), errs)
+    bad = {k: e for k, e in errs.items() if not e < tol}
+    assert not bad, f"rel_l2 above {tol}: {bad}\nall: {errs}"
     return errs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The fp32 precision mode: BASELINE.json's "rel 1e-3 for the fp32-accumulate path" (split-operand tensor-core GEMMs,
+# fp32 intermediates, fp32 attention; csrc/crf_precise.cu).  Same cases as the bf16 tier, tolerance 1e-3 on the output,
+# dx, dv and every one of the 13 parameter gradients.
+# ---------------------------------------------------------------------------------------------------------------------
+TOL_FP32 = 1e-3
+
+
+@pytest.mark.parametrize("shift", [0, 3])
+@pytest.mark.parametrize("strided", [False, True])
+def test_fp32_mode_config1_block_vs_oracle_cpu(shift, strided):
+    """BASELINE.json configs[0] in the fp32 mode against the fp32 CPU oracle."""
+    _run_block_vs_oracle(2, 60, 80, 128, 4, shift, seed=10 + shift, strided=strided, oracle_device="cpu",
+                         precision="fp32", tol=TOL_FP32)
+
+
+@pytest.mark.parametrize("H,W,C,nH,B", [(120, 160, 128, 4, 8), (60, 80, 256, 8, 2), (30, 40, 512, 16, 2), (15, 20, 1024, 32, 8),
+                                        (9, 10, 64, 4, 2), (9, 10, 64, 1, 2), (16, 23, 256, 2, 1), (1, 1, 64, 2, 1)])
+def test_fp32_mode_shapes_vs_oracle(H, W, C, nH, B):
+    """Decoder-scale shapes of configs[1], head widths 16 / 32 / 64 / 128, ragged maps; shifted windows."""
+    _run_block_vs_oracle(B, H, W, C, nH, 3, seed=500 + C + H, strided=True, oracle_device=DEV, precision="fp32", tol=TOL_FP32)
+
+
+@pytest.mark.parametrize("name", LAYER_CASES + HEAD_CASES)
+def test_fp32_mode_layer_matches_reference_golden(name):
+    """The reference's own golden vectors (whole BasicCRFLayer: both blocks, strided NCHW-view inputs) at rel 1e-3."""
+    g = load_golden(name)
+    (B, H, W, C, nH, depth), x, v, _ = golden_layer_inputs(g, DEV)
+    layer = _layer_from_golden(g, C, nH, depth)
+    layer.precision = "fp32"
+    x = x.detach().requires_grad_(True)
+    v = v.detach().requires_grad_(True)
+    y = layer(x, v, H, W)[0]
+    y.backward(torch.from_numpy(g["dy"]).to(DEV))
+    torch.cuda.synchronize()
+    errs = {"y": rel_l2(y.detach(), g["y"]), "dx": rel_l2(x.grad, g["dx"]), "dv": rel_l2(v.grad, g["dv"])}
+    for k, p in layer.named_parameters():
+        errs[k] = rel_l2(p.grad, g["grad." + k])
+    _report("golden fp32-mode " + name, errs)
+    bad = {k: e for k, e in errs.items() if not e < TOL_FP32}
+    assert not bad, f"rel_l2 above {TOL_FP32}: {bad}\nall: {errs}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CRFBlock.forward(x, v, mask_matrix): a mask other than the standard one is honoured (newcrf_layers.py:195,225-236)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("H,W,C,nH", [(15, 20, 128, 4), (9, 10, 64, 1)])
+def test_block_honours_custom_mask_matrix(H, W, C, nH, precision):
+    gen = torch.Generator().manual_seed(77)
+    nW = (-(-H // 7)) * (-(-W // 7))
+    mask = torch.where(torch.rand(nW, 49, 49, generator=gen) < 0.3, -100.0, 0.0) + 0.5 * torch.randn(nW, 49, 49, generator=gen)
+    _run_block_vs_oracle(2, H, W, C, nH, 3, seed=700 + C, strided=True, oracle_device=DEV, precision=precision,
+                         tol=TOL if precision == "bf16" else TOL_FP32, mask=mask)
+
+
+def test_block_module_recognises_the_standard_mask():
+    """Handing CRFBlock.forward the mask BasicCRFLayer builds gives bit-identical results to passing None (closed form);
+    a different mask changes the result; an unshifted block ignores the argument, as the reference does."""
+    pkg = _pkg()
+    torch.manual_seed(3)
+    H, W, C, nH = 15, 20, 64, 2
+    x = torch.randn(2, H * W, C, device=DEV)
+    v = torch.randn(2, H, W, C, device=DEV)
+    std = torch.from_numpy(O.shift_mask(H, W, 7, 3)).to(DEV)
+    blk = pkg.CRFBlock(C, nH, C, shift_size=3).to(DEV)
+    blk.H, blk.W = H, W
+    with torch.no_grad():
+        y_none, y_std = blk(x, v, None), blk(x, v, std)
+        y_other = blk(x, v, torch.zeros_like(std))
+    assert torch.equal(y_none, y_std)
+    assert not torch.equal(y_none, y_other)
+    blk0 = pkg.CRFBlock(C, nH, C, shift_size=0).to(DEV)
+    blk0.H, blk0.W = H, W
+    with torch.no_grad():
+        assert torch.equal(blk0(x, v, None), blk0(x, v, torch.full_like(std, -3.0)))
 
 
 @pytest.mark.parametrize("shift", [0, 3])

@@ -90,6 +90,65 @@ def test_gemm_wgrad(M, N, K, split):
     _check(db - 1.0, A.float().sum(0), 2e-5, f"wgrad colsum {M}x{N}x{K} split {split}")
 
 
+@pytest.mark.parametrize("M,N,K,kind", [(300, 128, 128, "fprop"), (1000, 256, 512, "fprop"), (257, 64, 192, "fprop"),
+                                        (300, 128, 128, "dgrad"), (1000, 512, 128, "dgrad"), (90, 64, 1024, "dgrad"),
+                                        (128, 128, 1000, "wgrad"), (512, 128, 5000, "wgrad"), (64, 256, 333, "wgrad")])
+def test_gemm_split3_fp32_emulation(M, N, K, kind):
+    """crf_gemm_args.split3 (the fp32 precision mode, csrc/crf_precise.cu): operands stored as [hi | lo] bf16 pairs, the
+    product accumulates hi*hi + hi*lo + lo*hi in fp32.  Against a float64 product of the ORIGINAL fp32 matrices: rel
+    2e-5 (bf16 x bf16 alone gives 3e-3), for all three operand orientations, with bias / column sums."""
+    ops, L = _ops(), _L()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+
+    def split(t):   # (rows, cols) fp32 -> (rows, 2 cols) bf16 [hi | lo]
+        hi = t.to(torch.bfloat16)
+        lo = (t - hi.float()).to(torch.bfloat16)
+        return torch.cat([hi, lo], dim=1).contiguous()
+
+    if kind == "fprop":      # D = A W^T + b : A (M, K), W (N, K), both K-major
+        A, B_ = torch.randn(M, K, generator=g).to(DEV), (torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+        bias = torch.randn(N, generator=g).to(DEV)
+        out = torch.full((M, N), float("nan"), device=DEV)
+        a = L.GemmArgs()
+        As, Bs = split(A), split(B_)
+        ref = A.double() @ B_.double().t() + bias.double()
+        am, bm = 0, 0
+    elif kind == "dgrad":    # D = A W : A (M, K) K-major, W (K, N) MN-major
+        A, B_ = torch.randn(M, K, generator=g).to(DEV), (torch.randn(K, N, generator=g) * K ** -0.5).to(DEV)
+        bias = None
+        out = torch.full((M, N), float("nan"), device=DEV)
+        As, Bs = split(A), split(B_)
+        ref = A.double() @ B_.double()
+        am, bm = 0, 1
+    else:                    # D += A^T B : A (K, M), B (K, N), both MN-major, K = tokens (split-K), colsum = sum_k A
+        A, B_ = (torch.randn(K, M, generator=g) * K ** -0.5).to(DEV), torch.randn(K, N, generator=g).to(DEV)
+        bias = None
+        out = torch.zeros(M, N, device=DEV)
+        As, Bs = split(A), split(B_)
+        ref = A.double().t() @ B_.double()
+        am, bm = 1, 1
+    a = L.GemmArgs()
+    a.A, a.B, a.a_major, a.b_major = As.data_ptr(), Bs.data_ptr(), am, bm
+    a.M, a.N, a.K = M, N, K
+    a.epilogue = L.EPI_SPLITK_F32 if kind == "wgrad" else L.EPI_STORE_F32
+    a.out0, a.ld_out, a.scale, a.device, a.split3 = out.data_ptr(), N, 1.0, 0, 1
+    if bias is not None:
+        a.bias = bias.data_ptr()
+    colsum = None
+    if kind == "wgrad":
+        colsum = torch.zeros(M, device=DEV)
+        a.colsum = colsum.data_ptr()
+        need = L.lib().crf_gemm_workspace_bytes(M, N, 3 * K, 0)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=DEV)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    import ctypes as C
+    L.check(L.lib().crf_gemm(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "crf_gemm split3")
+    torch.cuda.synchronize()
+    _check(out, ref, 2e-5, f"gemm split3 {kind}")
+    if colsum is not None:
+        _check(colsum, A.double().sum(0), 2e-5, "gemm split3 colsum")
+
+
 def test_gemm_epilogues():
     ops, L = _ops(), _L()
     M, N, K = 333, 256, 128
