@@ -11,8 +11,28 @@ from oracle import crf_oracle as O
 from tests.helpers import HEAD_CASES, LAYER_CASES, golden_layer_inputs, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-2
+TOL = 2e-2          # BASELINE.json's bound of the bf16-I/O tier; kept for parameter gradients (worst measured 1.1e-2)
+TOL_Y = 6e-3        # forward output: worst measured 2.9e-3 (profiles/r02_parity_errs_*.jsonl)
+TOL_DXDV = 1.5e-2   # input gradients: worst measured 6.4e-3
+TOL_ROW = 2e-2      # per-token-row relative error of y / dx / dv: a defect confined to one window cannot hide in a
+                    # whole-tensor norm (rows are ~3e-3 .. 8e-3 off)
 DEV = "cuda"
+
+
+def _tol(key, tier=None):
+    """Bound for one compared quantity: ~3x the worst measured error of the bf16 tier, or the fp32 tier's bound."""
+    if tier is not None:
+        return tier
+    return TOL_Y if key == "y" else TOL_DXDV if key in ("dx", "dv") else TOL
+
+
+def _row_err(a, b):
+    """max over token rows of ||a_t - b_t|| / ||b_t|| (rows with a negligible reference norm are skipped)."""
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1, a.shape[-1])
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1, b.shape[-1])
+    nb = b.norm(dim=1)
+    keep = nb > 1e-3 * nb.mean()
+    return float(((a - b).norm(dim=1)[keep] / nb[keep]).max())
 
 
 def _report(case, errs):
@@ -60,8 +80,8 @@ def test_layer_matches_reference_golden(name):
     for k, p in layer.named_parameters():
         errs[k] = rel_l2(p.grad, g["grad." + k])
     _report("golden " + name, errs)
-    bad = {k: e for k, e in errs.items() if not e < TOL}
-    assert not bad, f"rel_l2 above {TOL}: {bad}\nall: {errs}"
+    bad = {k: e for k, e in errs.items() if not e < _tol(k)}
+    assert not bad, f"rel_l2 above the bound: {bad}\nall: {errs}"
 
 
 @pytest.mark.parametrize("with_norm,out_bf16", [(False, False), (True, False), (True, True)])
@@ -167,7 +187,7 @@ def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device, pr
     pc = {k: t.detach().clone().to(DEV).requires_grad_(True) for k, t in p.items()}
     xc = x.to(DEV)
     vc = v.to(DEV)
-    if strided:  # .to() keeps the permuted strides
+    if strided and H * W > 1:  # .to() keeps the permuted strides
         assert not xc.is_contiguous()
     xc = xc.detach().requires_grad_(True)
     vc = vc.detach().requires_grad_(True)
@@ -180,8 +200,12 @@ def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device, pr
         errs[k] = rel_l2(pc[k].grad, po[k].grad)
     _report(f"block B{B} {H}x{W} C{C} nH{nH} shift{shift} strided{int(strided)} oracle@{oracle_device}"
             + (f" precision={precision}" if precision else "") + (" custom-mask" if mask is not None else ""), errs)
-    bad = {k: e for k, e in errs.items() if not e < tol}
-    assert not bad, f"rel_l2 above {tol}: {bad}\nall: {errs}"
+    fp32 = precision == "fp32"
+    bad = {k: e for k, e in errs.items() if not e < (tol if (fp32 or tol != TOL) else _tol(k))}
+    assert not bad, f"rel_l2 above the bound: {bad}\nall: {errs}"
+    rows = {"y": _row_err(yc, yo), "dx": _row_err(xc.grad, xo.grad), "dv": _row_err(vc.grad, vo.grad)}
+    row_tol = 1e-3 if fp32 else TOL_ROW   # fp32 tier: the spec bound per row
+    assert all(e < row_tol for e in rows.values()), f"per-token-row error above {row_tol}: {rows}"
     return errs
 
 
@@ -190,7 +214,7 @@ def _run_block_vs_oracle(B, H, W, C, nH, shift, seed, strided, oracle_device, pr
 # fp32 intermediates, fp32 attention; csrc/crf_precise.cu).  Same cases as the bf16 tier, tolerance 1e-3 on the output,
 # dx, dv and every one of the 13 parameter gradients.
 # ---------------------------------------------------------------------------------------------------------------------
-TOL_FP32 = 1e-3
+TOL_FP32 = 1.5e-4   # BASELINE.json asks for rel 1e-3; measured worst 3.6e-5 (C = 1024), typical 1.2e-5: bound at ~4x
 
 
 @pytest.mark.parametrize("shift", [0, 3])
