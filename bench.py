@@ -72,6 +72,9 @@ def parse_args():
                          "vs_gpu_eager; SURVEY.md 8d, BASELINE.md 3)")
     ap.add_argument("--lib-adam", action="store_true",
                     help="use the library's one-launch Adam step (crf_adam_step) instead of torch's fused Adam; opt-in")
+    ap.add_argument("--bucket-mb", type=int, default=64, help="N>1: DDP gradient bucket size (MB)")
+    ap.add_argument("--no-comm-breakdown", action="store_true",
+                    help="N>1: skip the all-reduce measurements (alone / exposed / overlapped) and the config-4 strong-scaling block")
     ap.add_argument("--ddp-grad-bf16", action="store_true",
                     help="N>1: exchange the gradient buckets in bf16 (90 MB instead of 180 MB per step); off by default")
     ap.add_argument("--memory-format", default="channels_last", choices=["contiguous", "channels_last"],
@@ -233,10 +236,10 @@ def run_ours(args):
         side0 = torch.cuda.Stream()
         side0.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side0):
-            net = wrap_ddp(model, device, world, grad_dtype=grad_dtype)
+            net = wrap_ddp(model, device, world, grad_dtype=grad_dtype, bucket_cap_mb=args.bucket_mb)
         torch.cuda.current_stream().wait_stream(side0)
     else:
-        net = wrap_ddp(model, device, world, grad_dtype=grad_dtype)
+        net = wrap_ddp(model, device, world, grad_dtype=grad_dtype, bucket_cap_mb=args.bucket_mb)
     # same update as train.py:41 in one fused kernel; capturable so the step can live in a CUDA graph
     if args.lib_adam:   # opt-in: the library's Adam (training.LibAdam): correct on hardware (profiles/r01_hwcheck.txt), speed unmeasured
         from monocular_depth_estimation_b200.training import LibAdam
@@ -377,15 +380,80 @@ def run_ours(args):
     lib.crf_timing_report(buf, need + 16)
     kernels = json.loads(buf.value.decode())
 
+    # ---- N > 1: what the gradient exchange costs (all ranks take part; eager steps, CUDA events, max over ranks) ----
+    comm, config4 = None, None
+    if world > 1 and not args.no_comm_breakdown:
+        k = max(3, min(args.steps, 10))
+        ms_with = timed(step_eager, k) / k
+
+        def step_nosync():     # the same step without the all-reduce (gradients stay rank-local)
+            with net.no_sync():
+                return train_step(net, opt, image_d, depth_d)
+        for _ in range(2):
+            step_nosync()
+        ms_without = timed(step_nosync, k) / k
+        with torch.no_grad():  # the un-synchronised steps let the replicas drift apart: re-align them with rank 0
+            for p_ in model.parameters():
+                dist.broadcast(p_.data, 0)
+        step_eager()
+        nbytes = sum(p.numel() for p in model.parameters() if p.requires_grad) * (2 if args.ddp_grad_bf16 else 4)
+        flat = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+        def allreduce_alone():
+            dist.all_reduce(flat)
+        for _ in range(3):
+            allreduce_alone()
+        ms_alone = timed(allreduce_alone, 10) / 10
+        exposed = max(0.0, ms_with - ms_without)
+        comm = {"gradient_bytes": nbytes, "allreduce_alone_ms": ms_alone,
+                "allreduce_alone_busbw_gbs": 2.0 * (world - 1) / world * nbytes / (ms_alone * 1e-3) / 1e9,
+                "step_ms_eager_with_allreduce": ms_with, "step_ms_eager_without_allreduce": ms_without,
+                "exposed_ms": exposed, "overlapped_fraction": max(0.0, 1.0 - exposed / ms_alone) if ms_alone else None,
+                "bucket_mb": args.bucket_mb, "how": "eager steps (no CUDA graph): DDP step vs the same step under no_sync(), "
+                "and one all-reduce of the whole gradient volume alone; CUDA events, max over ranks"}
+        # BASELINE.json configs[3]: global batch 64 sharded over the ranks (strong scaling), eager DDP steps
+        gb = 64
+        if not args.global_batch and gb % world == 0:
+            Bs = gb // world
+            try:
+                img_s = torch.rand(Bs, 3, H, W, device=device).contiguous(memory_format=mf)
+                dep_s = torch.rand(Bs, 1, H, W, device=device)
+
+                def step_strong():
+                    return train_step(net, opt, img_s, dep_s)
+                for _ in range(3):
+                    step_strong()
+                ks = max(3, min(args.steps, 6))
+                ms_s = timed(step_strong, ks) / ks
+                config4 = {"global_batch": gb, "per_gpu_batch": Bs, "n_gpus": world, "ms_per_step": ms_s,
+                           "value": gb / (ms_s * 1e-3), "unit": UNIT, "scaling": "strong", "cuda_graph": False,
+                           "what": "BASELINE.json configs[3]: global batch 64 at 480x640 sharded over the ranks, "
+                                   "eager DDP steps (fwd + loss + bwd + NCCL all-reduce + Adam)"}
+                del img_s, dep_s
+            except Exception as exc:
+                config4 = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+
     def finish():
-        # With a captured DDP step the NCCL communicator is referenced by the CUDA graph and an orderly
-        # destroy_process_group() was observed to hang at exit (after the result had been produced): leave hard.
+        # Orderly exit: drop the captured graph (it references the NCCL communicator) before the process group goes.
+        # A watchdog ends the process if destroy_process_group() does not return (observed once with a captured DDP
+        # step in round 1; the result line has been printed by then).
+        nonlocal graph
         torch.cuda.synchronize()
-        if graph is not None and world > 1:
-            sys.stderr.flush()
-            os._exit(0)
         if world > 1:
+            import gc
+            import threading
+            graph = None
+            gc.collect()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            dog = threading.Timer(20.0, lambda: os._exit(0))
+            dog.daemon = True
+            dog.start()
+            dist.barrier()
             dist.destroy_process_group()
+            dog.cancel()
 
     if rank != 0:
         finish()
@@ -509,6 +577,16 @@ def run_ours(args):
                         us = k["total_ms"] / k["launches"] * 1e3
                         ent[tag] = {"avg_us": us, "gbs": k["bytes"] / us / 1e3, "frac_of_hbm_peak": k["bytes"] / us / 1e3 / peaks["hbm_gbs"],
                                     "tensor_tflops": k["flops"] / us / 1e6}
+            try:   # the same block in the fp32 precision mode (rel 1e-3 tier: split-operand GEMMs, fp32 attention)
+                blk.precision = "fp32"
+                for _ in range(2):
+                    blk_step()
+                ms_f = timed(blk_step, 5) / 5
+                ent["fp32_mode"] = {"ms_fwd_bwd": ms_f, "windows_per_s": nwin / (ms_f * 1e-3),
+                                    "algorithmic_tflops": fl / (ms_f * 1e-3) / 1e12,
+                                    "slowdown_vs_bf16_mode": ms_f / ms_eager}
+            except Exception as exc:
+                ent["fp32_mode"] = {"error": f"{type(exc).__name__}: {exc}"}
             crf_blocks.append(ent)
             del blk, xb, vb, gy
         roof["per_scale"] = [{"stage": e["stage"], "C": e["C"], "ms_fwd_bwd": e["ms_fwd_bwd"],
@@ -596,6 +674,10 @@ def run_ours(args):
         line["crf_blocks"] = crf_blocks
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if comm is not None:
+        line["allreduce"] = comm
+    if config4 is not None:
+        line["config4_strong"] = config4
     if gpu_eager is not None:
         line["gpu_eager_baseline"] = gpu_eager
         best = max((v["value"] for v in gpu_eager.values() if isinstance(v, dict) and "value" in v), default=None)

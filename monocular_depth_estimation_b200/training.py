@@ -56,7 +56,7 @@ def init_distributed():
     return rank, local_rank, world, device
 
 
-def wrap_ddp(model, device, world, grad_dtype=None):
+def wrap_ddp(model, device, world, grad_dtype=None, bucket_cap_mb=64):
     """The DDP wrapper `train.py` lacks: gradients are averaged with an NCCL all-reduce, bucketed and launched while
     backward is still running (crf3's 29 M parameters become ready first and are reduced under the rest).
 
@@ -80,7 +80,7 @@ def wrap_ddp(model, device, world, grad_dtype=None):
     if device.type == "cuda":
         # broadcast_buffers=False: BatchNorm running statistics stay rank-local (46 BN layers would otherwise add a
         # broadcast of ~140 small buffers to every forward); gradients are what is averaged.
-        net = DDP(model, device_ids=[device.index], bucket_cap_mb=64, broadcast_buffers=False,
+        net = DDP(model, device_ids=[device.index], bucket_cap_mb=bucket_cap_mb, broadcast_buffers=False,
                   gradient_as_bucket_view=os.environ.get("CRF_DDP_BUCKET_VIEW", "1") != "0")
     else:
         net = DDP(model)
@@ -118,10 +118,12 @@ def save_checkpoint(path, model, optimizer, epoch, loss):
                 "optimizer_state_dict": optimizer.state_dict(), "loss": loss_t}, path)
 
 
-def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
+def load_checkpoint(path, model, optimizer=None, map_location="cpu", trusted_pickle=False):
     """Resume as src/train.py:56-67 does: returns (epoch, loss).  Accepts checkpoints written by the reference loop
-    (same format and keys) and ones whose keys carry a DDP `module.` prefix."""
-    ck = torch.load(path, map_location=map_location, weights_only=False)
+    (same format and keys) and ones whose keys carry a DDP `module.` prefix.  The format holds tensors, ints and plain
+    dicts only, so the file is read with weights_only=True (no arbitrary unpickling); trusted_pickle=True is the explicit
+    opt-in for legacy files that need the full unpickler."""
+    ck = torch.load(path, map_location=map_location, weights_only=not trusted_pickle)
     sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["model_state_dict"].items()}
     _unwrap(model).load_state_dict(sd, strict=True)
     if optimizer is not None and "optimizer_state_dict" in ck:
@@ -222,6 +224,19 @@ class LibAdam(torch.optim.Optimizer):
                 self.state[p]["exp_avg_sq"] = flat_v[o:o + p.numel()].view_as(p)
                 o += n
         return ps
+
+    def state_dict(self):
+        """torch.optim.Adam's layout: an independent CPU fp32 scalar `step` per parameter (here all parameters of a
+        group share ONE device counter, which must not leak into a checkpoint as ~300 aliases of the same storage: a
+        torch.optim.Adam resumed from it would advance the shared tensor once per parameter) and no private keys in
+        param_groups.  A checkpoint written here therefore resumes in torch.optim.Adam (the reference loop) and here."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if "step" in st:
+                st["step"] = torch.tensor(float(st["step"]), dtype=torch.float32)
+        for grp in sd["param_groups"]:
+            grp.pop("_step", None)
+        return sd
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)

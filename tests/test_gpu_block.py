@@ -428,8 +428,54 @@ def test_config5_highres_inference_vs_oracle():
         blocks = [{k: p.detach() for k, p in blk.named_parameters()} for blk in layer.blocks]
         yo = torch.cat([O.basic_crf_layer(x[i:i + 4], v[i:i + 4], H, W, blocks, nH) for i in range(0, B, 4)])
     torch.cuda.synchronize()
-    err = rel_l2(y, yo)
-    _report("config5 B16 240x320 C128 inference", {"y": err})
+    err, row = rel_l2(y, yo), _row_err(y, yo)
+    _report("config5 B16 240x320 C128 inference", {"y": err, "y_row_max": row})
+    assert err < TOL_Y and row < TOL_ROW, (err, row)
+
+
+@pytest.mark.parametrize("H,W,C,nH", [(120, 160, 256, 8), (60, 80, 512, 16), (30, 40, 1024, 32)])
+def test_config5_other_scales_inference_vs_oracle(H, W, C, nH):
+    """configs[4] at the other three decoder scales (960x1280, batch 16: 6 624 / 1 728 / 480 windows per block)."""
+    pkg = _pkg()
+    torch.manual_seed(50 + C)
+    B = 16
+    layer = pkg.BasicCRFLayer(dim=C, depth=2, num_heads=nH, v_dim=C).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV).flatten(2).transpose(1, 2)
+    v = torch.randn(B, C, H, W, device=DEV).permute(0, 2, 3, 1)
+    with torch.no_grad():
+        y = layer(x, v, H, W)[0]
+        blocks = [{k: p.detach() for k, p in blk.named_parameters()} for blk in layer.blocks]
+        yo = torch.cat([O.basic_crf_layer(x[i:i + 4], v[i:i + 4], H, W, blocks, nH) for i in range(0, B, 4)])
+    torch.cuda.synchronize()
+    err, row = rel_l2(y, yo), _row_err(y, yo)
+    _report(f"config5 B16 {H}x{W} C{C} inference", {"y": err, "y_row_max": row})
+    assert err < TOL_Y and row < TOL_ROW, (err, row)
+
+
+def test_config5_whole_model_960x1280_vs_oracle_model():
+    """configs[4] through the WHOLE model (MobileNetV3-large encoder + all four decoder stages + head) at 960x1280:
+    the product model (eval, fp32 encoder / convs, CRF blocks on the library) against the oracle's restatement of the
+    reference model with the same state_dict, both on the GPU in fp32 (batch 2: the oracle materialises the 49 x 49
+    attention tensors)."""
+    from monocular_depth_estimation_b200.model import PTModel
+    from oracle.model_oracle import OraclePTModel
+    from tests.helpers import fill_by_name
+    conv_tf32, mm_tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # fp32 oracle, fp32 encoder
+    try:
+        ref = fill_by_name(OraclePTModel()).eval().to(DEV)
+        ours = fill_by_name(PTModel()).eval().to(DEV)
+        gen = torch.Generator().manual_seed(9)
+        img = torch.rand(2, 3, 960, 1280, generator=gen).to(DEV)
+        with torch.no_grad():
+            yo = ref(img)
+            yc = ours(img)
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, mm_tf32
+    assert yc.shape == yo.shape == (2, 1, 960, 1280)
+    err = rel_l2(yc, yo)
+    _report("config5 whole model 960x1280 B2", {"depth": err})
     assert err < TOL, err
 
 

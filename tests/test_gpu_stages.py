@@ -557,8 +557,17 @@ def test_lib_adam_matches_torch_adam():
         _check(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], 1e-5, "exp_avg_sq")
     assert float(oa.state[ours[0]]["step"]) == 6.0
     # torch's optimizer accepts our state (same layout), and ours accepts torch's
+    sd = oa.state_dict()
+    steps = [st["step"] for st in sd["state"].values()]
+    assert all(not s.is_cuda and float(s) == 6.0 for s in steps)                       # torch's layout: CPU scalars ...
+    assert len({s.data_ptr() for s in steps}) == len(steps)                             # ... one per parameter, no aliases
+    assert all("_step" not in grp for grp in sd["param_groups"])
     ob2 = torch.optim.Adam(ref, lr=1e-3)
-    ob2.load_state_dict(oa.state_dict())
+    ob2.load_state_dict(sd)
+    for b in ref:
+        b.grad = torch.ones_like(b)
+    ob2.step()                                                                          # torch advances each step by ONE
+    assert all(float(ob2.state[b]["step"]) == 7.0 for b in ref)
     oa2 = LibAdam(ours, lr=1e-3)
     oa2.load_state_dict(ob.state_dict())
     for a in ours:
