@@ -12,6 +12,8 @@
 // and barrier init / TMEM allocation / descriptor prefetch are paid once per SM instead of once per tile.
 // Barriers: full/empty[stages] (TMA <-> MMA), tmem_full[4] (MMA -> epilogue, tcgen05.commit), tmem_empty[4]
 // (epilogue -> MMA, 128 arrivals), aux[4] (TMA aux-slab loads of each group).
+#include <stdlib.h>
+
 #include "crf_gemm_epi.cuh"
 
 namespace crf {
@@ -42,7 +44,12 @@ template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                       const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep) {
+                       const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep,
+                       int splits) {
+  // splits > 1 (fp32-output epilogues only): every output tile is computed by `splits` work units, each over a
+  // contiguous range of K chunks, and every unit ADDS its fp32 tile into the (zero-filled) output with a TMA reduction;
+  // unit 0 of a tile also adds the bias / residual.  Used where the tile count quantises badly on the SM count
+  // (M = 2400 at the 1/32 scale: 152 tiles on 148 SMs = a whole second round for 4 tiles).
   using TR = EpiTraits<EPI>;
   using PL = Plan<EPI>;
   constexpr int kStages = PL::kStages, kRing = PL::kRing, kBarOff = PL::kBarOff, kNumBars = PL::kNumBars;
@@ -65,8 +72,10 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = N / BN;
   const int total_tiles = ((M + BM - 1) / BM) * n_tiles;
-  const int nk = (K + BK - 1) / BK;
-  const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int nk_all = (K + BK - 1) / BK;
+  const int nk_split = (nk_all + splits - 1) / splits;          // K chunks per work unit (the last one may be shorter)
+  const int total_units = total_tiles * splits;                 // unit u: tile u % total_tiles, split u / total_tiles
+  const int my_tiles = (total_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -99,9 +108,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (lane == 0) {
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int t = blockIdx.x + i * gridDim.x;
+        const int u = blockIdx.x + i * gridDim.x;
+        const int t = u % total_tiles, sp = u / total_tiles;
         const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int kc0 = sp * nk_split, kc1 = min(nk_all, kc0 + nk_split);
+        for (int kc = kc0; kc < kc1; ++kc, ++it) {
           const int s = it % kStages;
           if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1);
           const uint32_t a_dst = base + s * kStage, b_dst = a_dst + kATile;
@@ -128,7 +139,9 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int sp = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) / total_tiles;
+        const int kc0 = sp * nk_split, kc1 = min(nk_all, kc0 + nk_split);
+        for (int kc = kc0; kc < kc1; ++kc, ++it) {
           const int s = it % kStages;
           mbar_wait(full_bar(s), (it / kStages) & 1);
           tc_fence_after();
@@ -138,7 +151,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t ad = make_smem_desc(a_src + ks * 32, 16, 1024, kSwizzle128);
             const uint64_t bd = (b_major == 0) ? make_smem_desc(b_src + ks * 32, 16, 1024, kSwizzle128)
                                                : make_smem_desc(b_src + ks * 2048, 8192, 1024, kSwizzle128);
-            umma_bf16(d_tmem, ad, bd, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, ad, bd, idesc, (kc > kc0 || ks > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
         }
@@ -155,10 +168,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int aux_cnt = 0;
     for (int i = g, n_i = 0; i < my_tiles; i += kAcc, ++n_i) {
-      const int t = blockIdx.x + i * gridDim.x;
+      const int u = blockIdx.x + i * gridDim.x;
+      const int t = u % total_tiles;
+      const bool first_split = u < total_tiles;   // the unit that also adds bias / residual
       const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
       const uint32_t taddr = tmem_base + g * BN + lane_base;
-      if (TR::kHasAux && r == 0) {  // first aux slab of the tile; the buffer was consumed before the last barrier
+      if (TR::kHasAux && first_split && r == 0) {  // first aux slab of the tile; the buffer was consumed before the last barrier
         mbar_expect_tx(aux_bar(g), kSlab);
         tma_load_2d(x_s, &tmAux, aux_bar(g), n0, m0);
       }
@@ -169,7 +184,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int nc = n0 + s * kSlabCols;
         if (r == 0) bulk_wait_read<0>();  // previous TMA store of this group has drained its slab buffers
         named_bar_sync(1 + g, 128);
-        if (TR::kHasAux) {
+        if (TR::kHasAux && first_split) {
           mbar_wait(aux_bar(g), aux_cnt & 1);
           ++aux_cnt;
         }
@@ -178,7 +193,15 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           uint32_t acc[32];
           tmem_ld32(taddr + s * kSlabCols + half * 32, acc);
           tmem_ld_wait();
-          epi_group32<EPI>(acc, ep, nc + half * 32, r, half, o0, xb);
+          if (TR::kOutF32 && !first_split) {   // later K splits contribute the bare partial product
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(o0 + sw128_offset(r, j)) =
+                  make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                              __uint_as_float(acc[4 * j + 3]));
+          } else {
+            epi_group32<EPI>(acc, ep, nc + half * 32, r, half, o0, xb);
+          }
         }
         if (s == kNumSlabs - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
@@ -187,10 +210,11 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         fence_proxy_async_smem();
         named_bar_sync(1 + g, 128);
         if (r == 0) {
-          if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s, nc, m0);
+          if (TR::kOutF32 && splits > 1) tma_reduce_add_2d(&tmO0, out0_s, nc, m0);
+          else if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s, nc, m0);
           if (TR::kHasOut1) tma_store_2d(&tmO1, x_s, nc, m0);
           bulk_commit();
-          if (TR::kHasAux && s + 1 < kNumSlabs) {
+          if (TR::kHasAux && first_split && s + 1 < kNumSlabs) {
             mbar_expect_tx(aux_bar(g), kSlab);
             tma_load_2d(x_s, &tmAux, aux_bar(g), nc + kSlabCols, m0);
           }
@@ -215,8 +239,21 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   constexpr int kSmemBytes = Plan<EPI>::kSmemBytes;
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
-  int grid = num_sms(a.device);
-  if (grid > tiles) grid = tiles;
+  const int sms = num_sms(a.device);
+  // K splits for the fp32-output epilogues when the tile count quantises badly on the SM count: pick the split count
+  // (<= 4, >= 512 K elements per unit) that minimises rounds / splits.  CRF_GEMM_SPLITK=0 turns it off.
+  int splits = 1;
+  if (EpiTraits<EPI>::kOutF32 && tiles >= sms / 2) {
+    static const bool on = !(getenv("CRF_GEMM_SPLITK") && atoi(getenv("CRF_GEMM_SPLITK")) == 0);
+    double best = static_cast<double>((tiles + sms - 1) / sms);
+    for (int s = 2; on && s <= 4 && a.K / s >= 512; ++s) {
+      const double cost = static_cast<double>((tiles * s + sms - 1) / sms) / s + 0.04 * (s - 1);  // + per-unit overhead
+      if (cost < best - 1e-9) { best = cost; splits = s; }
+    }
+  }
+  if (splits > 1) CRF_CUDA(cudaMemsetAsync(a.out0, 0, static_cast<size_t>(a.M) * a.N * sizeof(float), st));
+  int grid = sms;
+  if (grid > tiles * splits) grid = tiles * splits;
   EpiParams ep{a.bias, a.scale, a.scale_cols, 0, a.out0 != nullptr ? 1 : 0, nullptr};
   const double mn = static_cast<double>(a.M) * a.N;
   const double out_bytes = EPI == CRF_EPI_STORE_BF16 ? 2 * mn
@@ -225,7 +262,7 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
                            : 4 * mn;
   KernelTimer tm(st, 2.0 * mn * a.K, 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
                  "gemm_%s_epi%d_M%d_N%d_K%d", a.b_major ? "dgrad" : "fprop", EPI, a.M, a.N, a.K);
-  kern<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep);
+  kern<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep, splits);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

@@ -53,7 +53,9 @@ def _rand_bf16(*shape, seed=0, scale=1.0):
 # GEMM: the three operand orientations
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (90, 128, 128), (300, 128, 128), (1000, 256, 512), (257, 64, 192),
-                                   (4800, 512, 128), (640, 1024, 256), (384, 128, 2048), (200, 256, 4096)])
+                                   (4800, 512, 128), (640, 1024, 256), (384, 128, 2048), (200, 256, 4096),
+                                   # 152 / 300 tiles on 148 SMs: the K-split work units with the TMA reduce-add
+                                   (2400, 1024, 4096), (2400, 1024, 1024), (9600, 512, 2048)])
 def test_gemm_fprop(M, N, K):
     ops, L = _ops(), _L()
     A, W = _rand_bf16(M, K, seed=1), _rand_bf16(N, K, seed=2, scale=K ** -0.5)
@@ -64,7 +66,8 @@ def test_gemm_fprop(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 128), (1000, 512, 128), (257, 128, 512),
-                                   (640, 256, 1024), (500, 2048, 512)])
+                                   (640, 256, 1024), (500, 2048, 512), (2400, 1024, 4096), (2400, 1024, 2048),
+                                   (9600, 512, 2048)])
 def test_gemm_dgrad(M, N, K):
     """dX = dY (M,K) @ W (K,N): B operand read MN-major from the (out,in) weight."""
     ops, L = _ops(), _L()
@@ -147,6 +150,20 @@ def test_gemm_split3_fp32_emulation(M, N, K, kind):
     _check(out, ref, 2e-5, f"gemm split3 {kind}")
     if colsum is not None:
         _check(colsum, A.double().sum(0), 2e-5, "gemm split3 colsum")
+
+
+@pytest.mark.parametrize("M,N,K", [(2400, 1024, 4096), (2400, 1024, 1024), (9600, 512, 2048)])
+def test_gemm_bias_residual_with_k_splits(M, N, K):
+    """fc2 / proj of the 1/32 and 1/16 decoder scales: out = A W^T + bias + residual with the output tile summed over
+    K-split work units by TMA reduce-adds (only the first unit adds bias and residual)."""
+    ops, L = _ops(), _L()
+    A, W = _rand_bf16(M, K, seed=11), _rand_bf16(N, K, seed=12, scale=K ** -0.5)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(A, W, M, N, K, epilogue=L.EPI_BIAS_RES_F32, out0=out, bias=bias, aux1=res)
+    torch.cuda.synchronize()
+    _check(out, A.float() @ W.float().t() + bias + res, 1e-5, f"bias+res {M}x{N}x{K}")
 
 
 def test_gemm_epilogues():
