@@ -344,6 +344,8 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
   {  // token-major projections with N % 128 == 0 run on the persistent kernel (crf_gemm_persist.cu)
     static const bool persist = !(getenv("CRF_GEMM_PERSIST") && atoi(getenv("CRF_GEMM_PERSIST")) == 0);
     if (persist && !a.split3) {
+      const int rc2 = launch_gemm_pair(a, st);
+      if (rc2 >= 0) return rc2;
       const int rc = launch_gemm_persistent(a, st);
       if (rc >= 0) return rc;
     }
