@@ -211,6 +211,10 @@ typedef struct crf_gemm_args {
 int crf_gemm(const crf_gemm_args* a, void* stream);
 /* workspace a CRF_EPI_SPLITK_F32 GEMM of this shape wants (0 when it runs as a single split) */
 size_t crf_gemm_workspace_bytes(int M, int N, int K, int device);
+/* Scratch (flags + one 256 x 256 fp32 partial tile per SM pair) that lets the fprop / dgrad GEMMs of the wide decoder
+ * scales (N % 256 == 0, K >= 512: the CTA-pair kernel) run STREAM-K: pass it as crf_gemm_args.workspace with a
+ * non-split-K epilogue.  Without it those GEMMs run whole tiles in rounds of (SMs / 2).  Contents are scratch. */
+size_t crf_gemm_streamk_bytes(int device);
 
 /* The MLP half of a block in ONE kernel (C = 128 or 256):  y = x1 + fc2(GELU(fc1(LayerNorm(x1))))
  * (replaces `x + self.mlp(self.norm2(x))`, /root/reference/src/newcrf_layers.py:255, Mlp.forward :21-27).

@@ -34,14 +34,67 @@ constexpr int kNumBars = 2 * kStages + 2 + 2 + 2;       // full, empty, tmem_ful
 constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
 
+// ---- work decomposition -------------------------------------------------------------------------------------------
+// classic : pair p takes whole tiles p, p + npairs, ...  (rounds of 74 tiles: 40 / 76 / 80 / 152 / 160 tiles quantise badly)
+// stream-K: the tiles x K-chunks sequence (tile-major) is cut into npairs equal contiguous ranges.  A range starts with
+//           the TAIL of a tile another pair began (a "contributor" piece: the fp32 partial accumulator goes to this pair's
+//           workspace slot, then a flag is released), continues with whole tiles and ends with the HEAD of a tile (an
+//           "owner" piece: after its own K chunks the pair adds the partials of the pairs that hold the rest of the tile,
+//           then runs the ordinary epilogue).  A contributor piece is always the FIRST piece of its pair and waits for
+//           nothing, an owner piece is the LAST of its pair, so the flags are long set when they are needed and no pair
+//           ever waits on a pair that waits (CTAs are dispatched in index order; all 74 pairs are resident).
+struct Piece {
+  int t, kc0, kc1;
+};
+// range boundary of pair p, snapped to a tile boundary when it would leave a piece of fewer than `snap` K chunks
+__device__ __forceinline__ int sk_bound(int p, int npairs, int total, int nk, int snap) {
+  int b = static_cast<int>(static_cast<long long>(p) * total / npairs);
+  const int rem = b % nk;
+  if (rem < snap) b -= rem;
+  else if (nk - rem < snap) b += nk - rem;
+  return b;
+}
+struct PieceIter {
+  int nk, tiles, pair, npairs, streamk, w, w1, i;
+  __device__ PieceIter(int nk_, int tiles_, int pair_, int npairs_, int streamk_, int snap)
+      : nk(nk_), tiles(tiles_), pair(pair_), npairs(npairs_), streamk(streamk_), w(0), w1(0), i(0) {
+    if (streamk) {
+      w = sk_bound(pair, npairs, tiles * nk, nk, snap);
+      w1 = sk_bound(pair + 1, npairs, tiles * nk, nk, snap);
+    }
+  }
+  __device__ bool next(Piece& p) {
+    if (!streamk) {
+      const int t = pair + i * npairs;
+      if (t >= tiles) return false;
+      ++i;
+      p.t = t; p.kc0 = 0; p.kc1 = nk;
+      return true;
+    }
+    if (w >= w1) return false;
+    p.t = w / nk;
+    p.kc0 = w - p.t * nk;
+    p.kc1 = min(nk, p.kc0 + (w1 - w));
+    w += p.kc1 - p.kc0;
+    return true;
+  }
+};
+constexpr int kMaxContrib = 8;
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                 const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep, int splits) {
-  // splits > 1 (fp32-output epilogues): work unit u = (tile u % total_tiles, K range u / total_tiles); every unit adds its
-  // fp32 tile into the zero-filled output with a TMA reduction, the first unit of a tile adds bias / residual -- the
-  // remedy for 40 or 80 pair tiles on 74 SM pairs (M = 2400 at the 1/32 scale).
+                 const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep, int streamk,
+                 int snap, float* sk_ws, uint32_t* sk_flags) {
   using TR = EpiTraits<EPI>;
   constexpr int kSlabCols = TR::kSlabCols;
   constexpr int kNumSlabs = 128 / kSlabCols;   // per epilogue group (128 of the 256 columns)
@@ -64,9 +117,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_tiles = N / PN;
   const int total_tiles = ((M + PM - 1) / PM) * n_tiles;
   const int nk_all = (K + BK - 1) / BK;
-  const int nk_split = (nk_all + splits - 1) / splits;
-  const int total_units = total_tiles * splits;
-  const int my_tiles = (total_units - pair + npairs - 1) / npairs;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -98,13 +148,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== TMA producer (both CTAs): A rows [m0 + 128 rank, +128), B columns [n0 + 128 rank, +128) =====
     if (lane == 0) {
       int it = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int u = pair + i * npairs;
-        const int t = u % total_tiles, sp = u / total_tiles;
+      PieceIter pit(nk_all, total_tiles, pair, npairs, streamk, snap);
+      Piece pc;
+      while (pit.next(pc)) {
+        const int t = pc.t;
         const int m0 = (t / n_tiles) * PM + 128 * static_cast<int>(rank);
         const int n0 = (t % n_tiles) * PN + 128 * static_cast<int>(rank);
-        const int kc0 = sp * nk_split, kc1 = min(nk_all, kc0 + nk_split);
-        for (int kc = kc0; kc < kc1; ++kc, ++it) {
+        for (int kc = pc.kc0; kc < pc.kc1; ++kc, ++it) {
           const int s = it % kStages;
           if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1);
           const uint32_t a_dst = base + s * kStage, b_dst = a_dst + kATile;
@@ -124,15 +174,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc(1u, 0u, static_cast<uint32_t>(b_major), PM, PN);
       int it = 0;
-      for (int i = 0; i < my_tiles; ++i) {
+      PieceIter pit(nk_all, total_tiles, pair, npairs, streamk, snap);
+      Piece pc;
+      for (int i = 0; pit.next(pc); ++i) {
         const int a = i & 1;
         if (i >= 2) {
           mbar_wait(tempty_bar(a), ((i >> 1) - 1) & 1);   // both CTAs' epilogues have drained this accumulator
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + a * PN;
-        const int sp = (pair + i * npairs) / total_tiles;
-        const int kc0 = sp * nk_split, kc1 = min(nk_all, kc0 + nk_split);
+        const int kc0 = pc.kc0, kc1 = pc.kc1;
         for (int kc = kc0; kc < kc1; ++kc, ++it) {
           const int s = it % kStages;
           mbar_wait(full_bar(s), (it / kStages) & 1);
@@ -159,26 +210,72 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* xb = o0 + kSlab;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int aux_cnt = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int u = pair + i * npairs;
-      const int t = u % total_tiles;
-      const bool first_split = u < total_tiles;
+    // stream-K partial slots: [pair][rank][group] x (32 column quads x 128 rows x float4) -- a warp's accesses are contiguous
+    constexpr int kSlotFloats = 128 * 128;
+    const int total_units = total_tiles * nk_all;
+    PieceIter pit(nk_all, total_tiles, pair, npairs, streamk, snap);
+    Piece pc;
+    for (int i = 0; pit.next(pc); ++i) {
+      const int t = pc.t;
+      const bool emits = pc.kc0 == 0;                  // this pair owns the tile: it runs the real epilogue
+      const bool head = emits && pc.kc1 < nk_all;      // ... after adding the partials of the pairs that finish the tile
       const int a = i & 1;
       const int m0 = (t / n_tiles) * PM + 128 * static_cast<int>(rank);
       const int n0 = (t % n_tiles) * PN + 128 * e;
       const uint32_t taddr = tmem_base + a * PN + e * 128 + lane_base;
-      if (TR::kHasAux && first_split && r == 0) {
+      if (TR::kHasAux && emits && r == 0) {
         mbar_expect_tx(aux_bar(e), kSlab);
         tma_load_2d(x_s, &tmAux, aux_bar(e), n0, m0);
       }
+      // contributors of an owner piece: the pairs whose (first) piece covers the rest of this tile
+      int n_contrib = 0;
+      const float* contrib[kMaxContrib];
+      if (head) {
+        const int tile_end = (t + 1) * nk_all;
+        int pos = t * nk_all + pc.kc1, q = pair + 1;
+        while (pos < tile_end && q < npairs && n_contrib < kMaxContrib) {
+          const int q0 = sk_bound(q, npairs, total_units, nk_all, snap), q1 = sk_bound(q + 1, npairs, total_units, nk_all, snap);
+          if (q1 > q0) {  // (empty ranges hold nothing)
+            const int slot = (q * 2 + static_cast<int>(rank)) * 2 + e;
+            if (r == 0) {
+              while (ld_acquire_gpu(sk_flags + slot) == 0u) __nanosleep(64);
+            }
+            contrib[n_contrib++] = sk_ws + static_cast<size_t>(slot) * kSlotFloats;
+            pos = min(q1, tile_end);
+          }
+          ++q;
+        }
+      }
       mbar_wait(tfull_bar(a), (i >> 1) & 1);
       tc_fence_after();
+      if (!emits) {
+        // ---- contributor piece: bare fp32 partial accumulator -> this pair's workspace slot, then release the flag ----
+        const int slot = (pair * 2 + static_cast<int>(rank)) * 2 + e;
+        float4* dst = reinterpret_cast<float4*>(sk_ws + static_cast<size_t>(slot) * kSlotFloats) + r;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(dst + (c * 8 + j) * 128, make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                                        __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(a), 0);
+        __threadfence();
+        named_bar_sync(1 + e, 128);
+        if (r == 0) st_release_gpu(sk_flags + slot, 1u);
+        continue;
+      }
 #pragma unroll 1
       for (int s = 0; s < kNumSlabs; ++s) {
         const int nc = n0 + s * kSlabCols;
         if (r == 0) bulk_wait_read<0>();
-        named_bar_sync(1 + e, 128);
-        if (TR::kHasAux && first_split) {
+        named_bar_sync(1 + e, 128);   // (also publishes thread 0's flag acquires of an owner piece to the group)
+        if (TR::kHasAux) {
           mbar_wait(aux_bar(e), aux_cnt & 1);
           ++aux_cnt;
         }
@@ -187,15 +284,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t acc[32];
           tmem_ld32(taddr + s * kSlabCols + half * 32, acc);
           tmem_ld_wait();
-          if (TR::kOutF32 && !first_split) {   // later K splits contribute the bare partial product
+          if (head) {
+            const int c4 = (s * kSlabCols + half * 32) / 4;
+            for (int k = 0; k < n_contrib; ++k) {
+              const float4* src = reinterpret_cast<const float4*>(contrib[k]) + r;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(o0 + sw128_offset(r, j)) =
-                  make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
-                              __uint_as_float(acc[4 * j + 3]));
-          } else {
-            epi_group32<EPI>(acc, ep, nc + half * 32, r, half, o0, xb);
+              for (int j = 0; j < 8; ++j) {
+                const float4 pv = __ldcg(src + (c4 + j) * 128);
+                acc[4 * j + 0] = __float_as_uint(__uint_as_float(acc[4 * j + 0]) + pv.x);
+                acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + pv.y);
+                acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + pv.z);
+                acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + pv.w);
+              }
+            }
           }
+          epi_group32<EPI>(acc, ep, nc + half * 32, r, half, o0, xb);
         }
         if (s == kNumSlabs - 1) {  // this warp has read its part of the accumulator: one arrival per warp on the leader
           tc_fence_before();
@@ -205,11 +308,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(1 + e, 128);
         if (r == 0) {
-          if (TR::kOutF32 && splits > 1) tma_reduce_add_2d(&tmO0, out0_s, nc, m0);
-          else if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s, nc, m0);
+          if (EPI != CRF_EPI_BIAS_GELU || ep.store_out0) tma_store_2d(&tmO0, out0_s, nc, m0);
           if (TR::kHasOut1) tma_store_2d(&tmO1, x_s, nc, m0);
           bulk_commit();
-          if (TR::kHasAux && first_split && s + 1 < kNumSlabs) {
+          if (TR::kHasAux && s + 1 < kNumSlabs) {
             mbar_expect_tx(aux_bar(e), kSlab);
             tma_load_2d(x_s, &tmAux, aux_bar(e), nc + kSlabCols, m0);
           }
@@ -234,22 +336,29 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int tiles = ((a.M + PM - 1) / PM) * (a.N / PN);
   const int max_pairs = num_sms(a.device) / 2;
-  // K splits (fp32-output epilogues, >= 8 K chunks per unit): minimise rounds / splits.  MEASURED on B200 (round 2): no
-  // gain at M = 2400 (d fc1 29.4 us with and without) and a loss at M = 9600 (fc2 35.9 -> 42.7 us): the per-unit
-  // epilogue and the fp32 reduce-add traffic outweigh the better wave packing of 256 x 256 tiles -> off unless
-  // CRF_GEMM_PAIR_SPLITK=1.
-  int splits = 1;
-  if (EpiTraits<EPI>::kOutF32) {
-    static const bool on = getenv("CRF_GEMM_PAIR_SPLITK") && atoi(getenv("CRF_GEMM_PAIR_SPLITK")) != 0;
-    double best = static_cast<double>((tiles + max_pairs - 1) / max_pairs);
-    for (int s = 2; on && s <= 8 && a.K / s >= 512; ++s) {
-      const double cost = static_cast<double>((tiles * s + max_pairs - 1) / max_pairs) / s + 0.03 * (s - 1);
-      if (cost < best - 1e-9) { best = cost; splits = s; }
+  const int nk = (a.K + BK - 1) / BK;
+  int pairs = max_pairs;
+  if (pairs > tiles) pairs = tiles;
+  // Stream-K (see the kernel) runs when the caller hands over the partial-tile workspace (gemm_pair_streamk_bytes) and
+  // a pair's share is at least a quarter of a tile's K loop (<= 5 contributors per tile).  MEASURED on B200 (round 2,
+  // profiles/r02_gemm_streamk.md): bit-stable and correct, but NOT faster -- with all 74 pairs busy the time per K chunk
+  // doubles (0.45 -> 0.8 us): these GEMMs are bound by the L2 -> SM operand traffic (tiles x K chunks x 64 KB at
+  // ~5.5-6 TB/s), not by how the tiles pack into rounds.  So the block orchestration passes the workspace only with
+  // CRF_GEMM_STREAMK=1; through the C ABI (crf_gemm) the workspace itself is the switch.
+  int streamk = 0, snap = 1;
+  float* sk_ws = nullptr;
+  uint32_t* sk_flags = nullptr;
+  if (a.workspace != nullptr && a.workspace_bytes >= gemm_pair_streamk_bytes(a.device)) {
+    const double per_pair = static_cast<double>(tiles) * nk / max_pairs;
+    if (per_pair * 4.0 >= nk && per_pair >= 4.0) {
+      streamk = 1;
+      pairs = max_pairs;
+      snap = nk / 8 < 1 ? 1 : (nk / 8 > 4 ? 4 : nk / 8);
+      sk_flags = reinterpret_cast<uint32_t*>(a.workspace);
+      sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + 4096);
+      CRF_CUDA(cudaMemsetAsync(sk_flags, 0, 4096, st));
     }
   }
-  if (splits > 1) CRF_CUDA(cudaMemsetAsync(a.out0, 0, static_cast<size_t>(a.M) * a.N * sizeof(float), st));
-  int pairs = max_pairs;
-  if (pairs > tiles * splits) pairs = tiles * splits;
   EpiParams ep{a.bias, a.scale, a.scale_cols, 0, a.out0 != nullptr ? 1 : 0, nullptr, 0};
   const double mn = static_cast<double>(a.M) * a.N;
   const double out_bytes = EPI == CRF_EPI_STORE_BF16 ? 2 * mn
@@ -257,7 +366,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                            : EPI == CRF_EPI_BIAS_GELU ? (a.out0 != nullptr ? 4 * mn : 2 * mn)
                            : 4 * mn;
   KernelTimer tm(st, 2.0 * mn * a.K, 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
-                 "gemm2_%s_epi%d_M%d_N%d_K%d", a.b_major ? "dgrad" : "fprop", EPI, a.M, a.N, a.K);
+                 "gemm2%s_%s_epi%d_M%d_N%d_K%d", streamk ? "sk" : "", a.b_major ? "dgrad" : "fprop", EPI, a.M, a.N, a.K);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);
@@ -270,12 +379,18 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CRF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep, splits));
+  CRF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep, streamk, snap,
+                                sk_ws, sk_flags));
   note_launch();
   return 0;
 }
 
 }  // namespace
+
+// flags (4 KB) + one 256 x 256 fp32 partial tile per SM pair
+size_t gemm_pair_streamk_bytes(int device) {
+  return 4096 + static_cast<size_t>(num_sms(device) / 2) * PM * PN * sizeof(float);
+}
 
 // fprop / dgrad (A K-major) with N a multiple of 256 and enough work for CTA pairs.  Returns -1 if not eligible.
 int launch_gemm_pair(const crf_gemm_args& a, cudaStream_t st) {

@@ -72,6 +72,7 @@ long long launch_count();
 int launch_gemm(const crf_gemm_args& a, cudaStream_t st);
 int launch_gemm_persistent(const crf_gemm_args& a, cudaStream_t st);  // -1: shape not eligible
 int launch_gemm_pair(const crf_gemm_args& a, cudaStream_t st);        // cta_group::2 tiles (crf_gemm_pair.cu); -1: not eligible
+size_t gemm_pair_streamk_bytes(int device);   // workspace (crf_gemm_args.workspace) that lets the pair kernel run stream-K
 // crf_precise.cu: the fp32 precision mode (crf_block_desc.precision == CRF_PREC_FP32)
 size_t precise_saved_bytes(const crf_block_desc& d);
 size_t precise_bwd_bytes(const crf_block_desc& d);
