@@ -494,7 +494,7 @@ def run_ours(args):
         params = 11 * Cd * Cd + 12 * Cd + 169 * nH
         return n_windows(Hs, Ws) * 49 * 8 * Cd * 2 + 3 * params * 4
 
-    BLOCK_PREFIXES = ("gemm_", "attn_", "ln_fwd", "ln_bwd", "cast4", "cast_bf16", "convert_bf16", "mlp_fused", "splitk_reduce")
+    BLOCK_PREFIXES = ("gemm_", "gemm2", "dgrad_lnbwd", "attn_", "ln_fwd", "ln_bwd", "cast4", "cast_bf16", "convert_bf16", "mlp_fused", "splitk_reduce")
     blk_k = [k for k in kernels if k["kernel"].startswith(BLOCK_PREFIXES)]
     blk_ms = sum(k["total_ms"] for k in blk_k) / args.steps                       # per step, all eight blocks
     blk_bytes = sum(k["bytes"] * k["launches"] for k in blk_k) / args.steps       # sum of per-kernel algorithmic bytes

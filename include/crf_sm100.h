@@ -241,6 +241,15 @@ int crf_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st, int64_t sc, i
 /* LayerNorm backward: dx = LN'(g) + dres; accumulates dgamma/dbeta (+=). g f32 (T,C), x f32 (T,C). */
 int crf_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres, float* dx,
                void* dx_bf16, float* dgamma, float* dbeta, int T, int C, int device, void* stream);
+/* Input-gradient GEMM of a projection fused with the LayerNorm backward of its input (C = 128 or 256, K % 64 == 0):
+ *   g = dy (T, K) * W (K, C);  dx = LN'(g; x, stats, gamma) + dres;  dgamma / dbeta are ACCUMULATED (+=).
+ * The backward of `self.norm2(x)` -> fc1 and of `self.norm1(x)` -> qk (/root/reference/src/newcrf_layers.py:208,255)
+ * without the fp32 (T, C) gradient of the normalised rows ever reaching HBM.
+ *   dy_bf16 bf16 (T, K); w_bf16 bf16 (K, C) = the Linear's weight (out, in); x f32 (T, C); stats f32 (T, 2);
+ *   dres f32 (T, C) or NULL; dx f32 (T, C) and / or dx_bf16 bf16 (T, C) (at least one). */
+int crf_dgrad_ln_bwd(const void* dy_bf16, const void* w_bf16, int K, const float* x, const float* stats,
+                     const float* gamma, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T,
+                     int C, int device, void* stream);
 /* Stand-alone LayerNorm over the channels of contiguous token rows: the `norm_crf` that closes a decoder stage
  * (replaces nn.LayerNorm in NewCRF.forward, /root/reference/src/newcrf_layers.py:430-431).
  *   x f32 (T, C) contiguous; y f32 or bf16 (T, C) (y_dtype = CRF_DT_F32 / CRF_DT_BF16: under bf16 autocast the next

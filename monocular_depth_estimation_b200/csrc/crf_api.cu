@@ -30,6 +30,13 @@ bool streamk_enabled() {
   return on;
 }
 
+// d fc1 / d qk GEMM with the LayerNorm backward in its epilogue (crf_dgrad_lnbwd.cu); CRF_FUSED_LNBWD=0 restores the
+// GEMM + ln_bwd kernel pairs
+bool fused_lnbwd_enabled() {
+  static const bool on = [] { const char* e = getenv("CRF_FUSED_LNBWD"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 bool x_is_plain(const crf_block_desc& d) {
   const int64_t T_img = static_cast<int64_t>(d.H) * d.W;
   return d.x_dtype == CRF_DT_F32 && d.x_stride_c == 1 && d.x_stride_t == d.C && d.x_stride_b == T_img * d.C;
@@ -283,9 +290,18 @@ static int block_bwd_impl(const crf_block_desc* d, const crf_block_params* p, co
   }
   if (gemm_dgrad(dyb, S + L.wb_fc2, T, 4 * C, C, CRF_EPI_MUL_DGELU, Wk + W.dhpre, S + L.pre, dev, st, sk_ws, sk_bytes)) return 1;
   if (gemm_wgrad(dyb, S + L.act, C, 4 * C, T, g->fc2_w, g->fc2_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (gemm_dgrad(Wk + W.dhpre, S + L.wb_fc1, T, C, 4 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st, sk_ws, sk_bytes)) return 1;
+  const bool fuse_ln = fused_lnbwd_enabled() && dgrad_lnbwd_supported(C, 2 * C);
+  if (fuse_ln) {  // dx1 = dy + LN2'(dhpre W1) straight from the GEMM's accumulator rows
+    if (launch_dgrad_lnbwd(Wk + W.dhpre, S + L.wb_fc1, 4 * C, reinterpret_cast<const float*>(S + L.x1),
+                           reinterpret_cast<const float*>(S + L.stats2), p->norm2_w, dy, dx1, Wk + W.dx1b, g->norm2_w,
+                           g->norm2_b, T, C, dev, st))
+      return 1;
+  } else {
+    if (gemm_dgrad(Wk + W.dhpre, S + L.wb_fc1, T, C, 4 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st, sk_ws, sk_bytes)) return 1;
+  }
   if (gemm_wgrad(Wk + W.dhpre, S + L.xn2, 4 * C, C, T, g->fc1_w, g->fc1_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_ln_bwd(dxn, reinterpret_cast<const float*>(S + L.x1), reinterpret_cast<const float*>(S + L.stats2),
+  if (!fuse_ln &&
+      launch_ln_bwd(dxn, reinterpret_cast<const float*>(S + L.x1), reinterpret_cast<const float*>(S + L.stats2),
                     p->norm2_w, dy, dx1, Wk + W.dx1b, g->norm2_w, g->norm2_b, T, C, st))
     return 1;
   // ---- attention ----
@@ -295,9 +311,16 @@ static int block_bwd_impl(const crf_block_desc* d, const crf_block_params* p, co
                       reinterpret_cast<const float*>(S + L.lse),
                       Wk + W.dob, Wk + W.dqk, dv, dv_accumulate, g->rpb_table, g->qk_b, st, /*ext_replaces=*/1))
     return 1;
-  if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st, sk_ws, sk_bytes)) return 1;
+  if (fuse_ln) {  // dx = dx1 + LN1'(dqk Wqk)
+    if (launch_dgrad_lnbwd(Wk + W.dqk, S + L.wb_qk, 2 * C, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w,
+                           dx1, dx, dx_bf16, g->norm1_w, g->norm1_b, T, C, dev, st))
+      return 1;
+  } else {
+    if (gemm_dgrad(Wk + W.dqk, S + L.wb_qk, T, C, 2 * C, CRF_EPI_STORE_F32, dxn, nullptr, dev, st, sk_ws, sk_bytes)) return 1;
+  }
   if (gemm_wgrad(Wk + W.dqk, S + L.xn1, 2 * C, C, T, g->qk_w, g->qk_b, Wk + W.partials, W.partials_bytes, dev, st)) return 1;
-  if (launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, dx_bf16,
+  if (!fuse_ln &&
+      launch_ln_bwd(dxn, x_tok, reinterpret_cast<const float*>(S + L.stats1), p->norm1_w, dx1, dx, dx_bf16,
                     g->norm1_w, g->norm1_b, T, C, st))
     return 1;
   return 0;
@@ -502,6 +525,15 @@ int crf_shift_mask(float* mask, int H, int W, int window, int shift, void* strea
 
 size_t crf_gemm_workspace_bytes(int M, int N, int K, int device) {
   return gemm_splitk_workspace_bytes(M, N, K, device, nullptr);
+}
+
+int crf_dgrad_ln_bwd(const void* dy_bf16, const void* w_bf16, int K, const float* x, const float* stats,
+                     const float* gamma, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T,
+                     int C, int device, void* stream) {
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_dgrad_lnbwd(dy_bf16, w_bf16, K, x, stats, gamma, dres, dx, dx_bf16, dgamma, dbeta, T, C, device,
+                            static_cast<cudaStream_t>(stream));
 }
 
 size_t crf_gemm_streamk_bytes(int device) { return gemm_pair_streamk_bytes(device); }

@@ -90,6 +90,11 @@ int launch_ln_fwd(const void* x, int x_dtype, int64_t sb, int64_t st_, int64_t s
                   cudaStream_t st);
 int launch_ln_bwd(const float* g, const float* x, const float* stats, const float* gamma, const float* dres,
                   float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
+// crf_dgrad_lnbwd.cu: input-gradient GEMM + LayerNorm backward of that input in one kernel (C = 128, 256)
+bool dgrad_lnbwd_supported(int C, int K);
+int launch_dgrad_lnbwd(const void* dY, const void* W, int K, const float* x, const float* stats, const float* gamma,
+                       const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int T, int C, int device,
+                       cudaStream_t st);
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
                          float* stats, int T, int C, cudaStream_t st);
 int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,

@@ -269,7 +269,7 @@ ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, int T) {
   constexpr int C = 64 * NCH;
-  __shared__ float red[8][64];
+  __shared__ __align__(16) float red[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2 gam[NCH], dga[NCH], dbe[NCH];
 #pragma unroll
@@ -319,11 +319,19 @@ ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float
       red[warp][2 * lane] = v.x;
       red[warp][2 * lane + 1] = v.y;
       __syncthreads();
-      if (threadIdx.x < 64) {
-        float s = 0.f;
+      if (threadIdx.x < 16) {  // four columns per thread, one vector reduction: 4x fewer atomic operations per CTA
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        atomicAdd((pass == 0 ? dgamma : dbeta) + 64 * k + threadIdx.x, s);
+        for (int w = 0; w < 8; ++w) {
+          const float4 v = *reinterpret_cast<const float4*>(&red[w][4 * threadIdx.x]);
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float* dst = (pass == 0 ? dgamma : dbeta) + 64 * k + 4 * threadIdx.x;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          red_add_f32x4(dst, s);
+        } else {  // gradient buffers that are unaligned views (DDP buckets)
+          atomicAdd(dst, s.x); atomicAdd(dst + 1, s.y); atomicAdd(dst + 2, s.z); atomicAdd(dst + 3, s.w);
+        }
       }
       __syncthreads();
     }
@@ -331,35 +339,60 @@ ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// out[n] += sum_t g[t,n], g bf16 (T,N).  Thread owns two adjacent columns; CTA covers 512 columns x a row chunk.
+// out[n] += sum_t g[t,n], g bf16 (T,N).  Thread owns eight adjacent columns (one 16-byte load per row) and keeps eight
+// rows in flight (128 B per thread, 32 KB per CTA); a CTA covers up to 2048 columns x a row chunk, the row lanes are
+// combined through shared memory, then two vector reductions per thread of row lane 0.  Two CTAs per SM: the atomics at
+// the end are per CTA, so more CTAs cost more than they hide (6 CTAs per SM: 2.5x slower at N >= 256, measured).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out, int T, int N, int rows_per_cta) {
-  // threadIdx.x: column quad (4 columns, one 8-byte load); threadIdx.y: row lane, so that narrow matrices (N = 128:
-  // 32 column threads) still keep 256 loads in flight per CTA; row lanes are combined through shared memory.
-  __shared__ float red[256][4];
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  __shared__ __align__(16) float red[256][8];
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(T, r0 + rows_per_cta);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
   if (c < N) {
+    const int by = blockDim.y;
+    const int64_t step = static_cast<int64_t>(by) * N;
     const __nv_bfloat16* p = g + static_cast<int64_t>(r0 + threadIdx.y) * N + c;
-    const int64_t step = static_cast<int64_t>(blockDim.y) * N;
-#pragma unroll 8
-    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y, p += step) {
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
-      s0 += bf16_lo(w.x); s1 += bf16_hi(w.x); s2 += bf16_lo(w.y); s3 += bf16_hi(w.y);
+    int r = r0 + threadIdx.y;
+    for (; r + 7 * by < r1; r += 8 * by, p += 8 * step) {
+      uint4 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(p + u * step));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s[0] += bf16_lo(w[u].x); s[1] += bf16_hi(w[u].x); s[2] += bf16_lo(w[u].y); s[3] += bf16_hi(w[u].y);
+        s[4] += bf16_lo(w[u].z); s[5] += bf16_hi(w[u].z); s[6] += bf16_lo(w[u].w); s[7] += bf16_hi(w[u].w);
+      }
+    }
+    for (; r < r1; r += by, p += step) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+      s[0] += bf16_lo(w.x); s[1] += bf16_hi(w.x); s[2] += bf16_lo(w.y); s[3] += bf16_hi(w.y);
+      s[4] += bf16_lo(w.z); s[5] += bf16_hi(w.z); s[6] += bf16_lo(w.w); s[7] += bf16_hi(w.w);
     }
   }
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  red[tid][0] = s0; red[tid][1] = s1; red[tid][2] = s2; red[tid][3] = s3;
+  *reinterpret_cast<float4*>(&red[tid][0]) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(&red[tid][4]) = make_float4(s[4], s[5], s[6], s[7]);
   __syncthreads();
   if (threadIdx.y == 0 && c < N) {
+    float4 a = make_float4(s[0], s[1], s[2], s[3]), b = make_float4(s[4], s[5], s[6], s[7]);
     for (int y = 1; y < blockDim.y; ++y) {
-      const float* q = red[y * blockDim.x + threadIdx.x];
-      s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3];
+      const float4 p = *reinterpret_cast<const float4*>(&red[y * blockDim.x + threadIdx.x][0]);
+      const float4 q = *reinterpret_cast<const float4*>(&red[y * blockDim.x + threadIdx.x][4]);
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+      b.x += q.x; b.y += q.y; b.z += q.z; b.w += q.w;
     }
-    atomicAdd(out + c, s0); atomicAdd(out + c + 1, s1); atomicAdd(out + c + 2, s2); atomicAdd(out + c + 3, s3);
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      red_add_f32x4(out + c, a);
+      red_add_f32x4(out + c + 4, b);
+    } else {
+      atomicAdd(out + c, a.x); atomicAdd(out + c + 1, a.y); atomicAdd(out + c + 2, a.z); atomicAdd(out + c + 3, a.w);
+      atomicAdd(out + c + 4, b.x); atomicAdd(out + c + 5, b.y); atomicAdd(out + c + 6, b.z); atomicAdd(out + c + 7, b.w);
+    }
   }
 }
 
@@ -384,7 +417,17 @@ __global__ void __launch_bounds__(256) cast4_bf16_kernel(const Cast4 c) {
   __nv_bfloat16* __restrict__ dst = c.dst[blockIdx.y];
   const long long n = c.n[blockIdx.y];
   const long long stride = static_cast<long long>(gridDim.x) * 256 * 4;
-  for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4; i < n; i += stride) {
+  long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  // four independent 16-byte loads in flight per thread (64 KB per CTA-quad): the one-load loop reached 2.7 TB/s
+  for (; i + 3 * stride + 3 < n; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + i + u * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      *reinterpret_cast<uint2*>(dst + i + u * stride) = make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
+  }
+  for (; i < n; i += stride) {
     if (i + 3 < n) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
       *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -558,16 +601,26 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
   CRF_CHECK(C % 64 == 0, "ln_bwd: C=%d must be a multiple of 64", C);
   int dev = 0;
   cudaGetDevice(&dev);
-  int blocks = (T + 7) / 8;
-  const int cap = num_sms(dev) * 8;
-  if (blocks > cap) blocks = cap;
+  // one warp per row, grid-stride; ONE resident wave of CTAs (occupancy x SMs): the wide rows (C >= 512: 100-170
+  // registers per thread, 1-2 CTAs per SM) otherwise ran 300 CTAs as 2.03 waves = 3 rounds of latency-bound work, and
+  // every CTA ends with 2 C column reductions into dgamma / dbeta
+  const int sms = num_sms(dev);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   KernelTimer tm(st, 0.0, static_cast<double>(T) * C * (12 + (dres != nullptr ? 4 : 0) + (dx_bf16 != nullptr ? 2 : 0)),
                  "ln_bwd_T%d_C%d", T, C);
 #define CRF_LNB(NCH)                                                                                         \
-  case NCH:                                                                                                  \
+  case NCH: {                                                                                                \
+    static int occ = 0;                                                                                      \
+    if (occ == 0) {                                                                                          \
+      int o = 0;                                                                                             \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ln_bwd_kernel<NCH, float>, 256, 0) != cudaSuccess || o < 1) o = 1; \
+      occ = o > 8 ? 8 : o;                                                                                   \
+    }                                                                                                        \
+    int blocks = (T + 7) / 8;                                                                                \
+    if (blocks > sms * occ) blocks = sms * occ;                                                              \
     ln_bwd_kernel<NCH><<<blocks, 256, 0, st>>>(g, x, stats, gamma, dres, dx, dxb, dgamma, dbeta, T);         \
-    break;
+    break;                                                                                                   \
+  }
   switch (C / 64) {
     CRF_LNB(1) CRF_LNB(2) CRF_LNB(3) CRF_LNB(4) CRF_LNB(5) CRF_LNB(6) CRF_LNB(7) CRF_LNB(8) CRF_LNB(9) CRF_LNB(10)
     CRF_LNB(11) CRF_LNB(12) CRF_LNB(13) CRF_LNB(14) CRF_LNB(15) CRF_LNB(16)
@@ -681,21 +734,21 @@ int launch_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int 
 }
 
 int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st) {
-  CRF_CHECK(N % 4 == 0, "colsum: N must be a multiple of 4");
+  CRF_CHECK(N % 8 == 0, "colsum: N must be a multiple of 8");
+  CRF_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "colsum: g must be 16-byte aligned");
   int dev = 0;
   cudaGetDevice(&dev);
-  int bx = N / 4;                       // column quads
+  int bx = N / 8;                       // column octets
   if (bx > 256) bx = 256;
   int bxp = 1;
   while (bxp < bx) bxp <<= 1;           // power of two so that bx * by == 256
   bx = bxp;
   const int by = 256 / bx;
-  const int gx = (N / 4 + bx - 1) / bx;
-  // two CTAs per SM: enough loads in flight for the HBM, few enough CTAs that the same-address atomics at the end
-  // (one per column and CTA) stay cheap
+  const int gx = (N / 8 + bx - 1) / bx;
+  // two CTAs per SM (see the kernel)
   int gy = (num_sms(dev) * 2 + gx - 1) / gx;
   int rows = (T + gy - 1) / gy;
-  if (rows < 32) rows = 32;
+  if (rows < 8 * by) rows = 8 * by;
   gy = (T + rows - 1) / rows;
   KernelTimer tm(st, 0.0, 2.0 * T * N, "colsum_T%d_N%d", T, N);
   colsum_bf16_kernel<<<dim3(gx, gy), dim3(bx, by), 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
@@ -728,7 +781,7 @@ int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long 
   int dev = 0;
   cudaGetDevice(&dev);
   long long gx = (nmax / 4 + 255) / 256;
-  const long long cap = num_sms(dev) * 4;
+  const long long cap = num_sms(dev) * 2;   // x 4 matrices (grid.y) = 8 CTAs per SM
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   KernelTimer tm(st, 0.0, 6.0 * total, "cast4_bf16_n%lld", total);

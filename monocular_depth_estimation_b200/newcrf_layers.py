@@ -220,7 +220,7 @@ class _ConvBiasFn(torch.autograd.Function):
     def backward(ctx, g):
         Cd = g.shape[1]
         if (g.is_cuda and g.dtype == torch.bfloat16 and g.is_contiguous(memory_format=torch.channels_last)
-                and Cd % 4 == 0):
+                and Cd % 8 == 0):
             from . import ops
             db = ops.colsum_bf16(g.permute(0, 2, 3, 1).reshape(-1, Cd))
         else:

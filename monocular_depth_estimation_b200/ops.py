@@ -147,6 +147,22 @@ def ln_bwd(g, x, stats, gamma, dres=None, want_bf16=False):
     return dx, dxb, dgamma, dbeta
 
 
+def dgrad_ln_bwd(dy_bf16, w_bf16, x, stats, gamma, dres=None, want_f32=True, want_bf16=True):
+    """dx = LN'(dy @ W; x, stats, gamma) + dres in one kernel (crf_dgrad_ln_bwd; C = 128 / 256).
+    dy_bf16 (T, K), w_bf16 (K, C) -> (dx f32 or None, dx bf16 or None, dgamma, dbeta)."""
+    T, K = dy_bf16.shape
+    Cd = w_bf16.shape[1]
+    dev = x.device
+    dx = torch.empty(T, Cd, dtype=torch.float32, device=dev) if want_f32 else None
+    dxb = torch.empty(T, Cd, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    dgamma = torch.zeros(Cd, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(Cd, dtype=torch.float32, device=dev)
+    L.check(L.lib().crf_dgrad_ln_bwd(_ptr(dy_bf16), _ptr(w_bf16), K, _ptr(x), _ptr(stats), _ptr(gamma), _ptr(dres),
+                                     _ptr(dx), _ptr(dxb), _ptr(dgamma), _ptr(dbeta), T, Cd, _dev(x), _stream(x)),
+            "crf_dgrad_ln_bwd")
+    return dx, dxb, dgamma, dbeta
+
+
 def colsum_bf16(g):
     T, N = g.shape
     out = torch.zeros(N, dtype=torch.float32, device=g.device)

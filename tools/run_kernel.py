@@ -30,7 +30,7 @@ def timed(fn, iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "block", "gemm", "gemms", "mlp"])
+    ap.add_argument("what", choices=["attn", "block", "gemm", "gemms", "mlp", "lnbwd", "misc"])
     ap.add_argument("--infer", action="store_true", help="mlp: inference mode (no saved tensors)")
     ap.add_argument("--stage", type=int, default=0)
     ap.add_argument("--batch", type=int, default=8)
@@ -101,6 +101,40 @@ def main():
             y = blk(x, v, None)
             y.backward(torch.ones_like(y))
         print("block fwd+bwd ms", timed(step, a.iters))
+    elif a.what == "misc":
+        # the memory-bound helpers of a stage: LayerNorm backward, conv-bias column sums, weight casts
+        g = torch.randn(T, C, device=dev)
+        xx = torch.randn(T, C, device=dev)
+        stats = torch.stack([xx.mean(1), (xx.var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
+        gam = torch.ones(C, device=dev)
+        dres = torch.randn(T, C, device=dev)
+        ms = timed(lambda: ops.ln_bwd(g, xx, stats, gam, dres, want_bf16=True), a.iters)
+        print(f"ln_bwd  T{T} C{C}: {ms*1e3:7.1f} us  {T*C*18/ms/1e6:7.0f} GB/s")
+        gb = torch.randn(T, C, device=dev).to(torch.bfloat16)
+        ms = timed(lambda: ops.colsum_bf16(gb), a.iters)
+        print(f"colsum  T{T} N{C}: {ms*1e3:7.1f} us  {T*C*2/ms/1e6:7.0f} GB/s")
+        w = torch.randn(11 * C * C, device=dev)
+        ms = timed(lambda: ops.cast_bf16(w), a.iters)
+        print(f"cast    n{w.numel()}: {ms*1e3:7.1f} us  {w.numel()*6/ms/1e6:7.0f} GB/s")
+    elif a.what == "lnbwd":
+        # d fc1 / d qk + LayerNorm backward: fused kernel against the GEMM + ln_bwd pair
+        for name, K in (("d_fc1+LN2'", 4 * C), ("d_qk+LN1'", 2 * C)):
+            dy = torch.randn(T, K, device=dev).to(torch.bfloat16)
+            Wt = (torch.randn(K, C, device=dev) * K ** -0.5).to(torch.bfloat16)
+            xx = torch.randn(T, C, device=dev)
+            stats = torch.stack([xx.mean(1), (xx.var(1, unbiased=False) + 1e-5).rsqrt()], 1).contiguous()
+            gam = torch.ones(C, device=dev)
+            dres = torch.randn(T, C, device=dev)
+            gx = torch.empty(T, C, device=dev)
+            ms_f = timed(lambda: ops.dgrad_ln_bwd(dy, Wt, xx, stats, gam, dres), a.iters)
+
+            def two():
+                ops.gemm(dy, Wt, T, C, K, a_major=0, b_major=1, epilogue=L.EPI_STORE_F32, out0=gx)
+                ops.ln_bwd(gx, xx, stats, gam, dres, want_bf16=True)
+            ms_2 = timed(two, a.iters)
+            mb = T * (2.0 * K + 14.0 * C) / 1e6
+            print(f"{name:12s} T{T} C{C} K{K}: fused {ms_f*1e3:7.1f} us ({mb/ms_f/1e3:6.0f} GB/s on {mb:.0f} MB)   "
+                  f"GEMM + ln_bwd {ms_2*1e3:7.1f} us")
     elif a.what == "gemms":
         # every fprop / dgrad projection shape of this stage: (label, M, N, K, b_major, epilogue)
         shapes = [("qk", T, 2 * C, C, 0, L.EPI_STORE_BF16), ("proj+res", T, C, C, 0, L.EPI_BIAS_RES_F32),
