@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CRF_ABI_VERSION 2
+#define CRF_ABI_VERSION 3
 enum { CRF_PREC_BF16 = 0, CRF_PREC_FP32 = 1 };
 
 enum { CRF_DT_F32 = 0, CRF_DT_BF16 = 1 };
@@ -145,6 +145,10 @@ typedef struct crf_layer_args {
   const crf_block_params* params;  /* [depth] */
   const float* norm_w;             /* closing LayerNorm weight (C) or NULL */
   const float* norm_b;
+  int32_t out_shuffle;             /* 1: the closing LayerNorm writes y with the decoder's PixelShuffle(2) folded in
+                                    * (/root/reference/src/model_mobileV3_large_newCRFs.py:116-120): y and dy are
+                                    * (B, 2H, 2W, C/4) NHWC maps, y[b, 2h+i, 2w+j, k] = LN(x)[b, h*W+w, 4k+2i+j].
+                                    * Needs the closing norm.  (ABI 3) */
 } crf_layer_args;
 int crf_layer_sizes(const crf_block_desc* d, int depth, int with_norm, size_t* saved_bytes, size_t* ws_bwd_bytes);
 int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* x, const void* v, void* y, void* saved,
@@ -259,6 +263,13 @@ int crf_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
                       float* stats, int T, int C, int device, void* stream);
 int crf_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
                       float* dgamma, float* dbeta, int T, int C, int device, void* stream);
+/* The same LayerNorm with the PixelShuffle(2) that follows a decoder stage folded into its store (forward) / load
+ * (backward): x, dx f32 (B*H*W, C) token rows; y, g (B, 2H, 2W, C/4) NHWC, y[b, 2h+i, 2w+j, k] = LN(x)[(b,h,w), 4k+2i+j]
+ * -- bit-identical to crf_layernorm_fwd followed by crf_pixel_shuffle_nhwc. */
+int crf_layernorm_ps_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                         float* stats, int B, int H, int W, int C, int device, void* stream);
+int crf_layernorm_ps_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                         float* dgamma, float* dbeta, int B, int H, int W, int C, int device, void* stream);
 /* The training loop's loss, 1.0 * SSIM + 0.1 * L1 (replaces /root/reference/src/train.py:94-100 with the SSIM module of
  * /root/reference/src/loss.py:57-88: reflection pad 1, 3x3 average pools, clamp((1 - n/d) / 2, 0, 1), mean).
  *   pred f32 or bf16 (n_img, H, W) contiguous (n_img = batch x channels), target f32, H, W >= 2.

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "crf_last_error", "crf_abi_version", "crf_kernel_launches", "crf_timing_enable", "crf_timing_report", "crf_block_sizes", "crf_block_fwd", "crf_block_bwd", "crf_convert_v",
     "crf_layer_sizes", "crf_layer_fwd", "crf_layer_bwd",
     "crf_window_gather", "crf_window_scatter", "crf_shift_mask", "crf_gemm", "crf_mlp_fwd", "crf_gemm_workspace_bytes", "crf_gemm_streamk_bytes", "crf_ln_fwd", "crf_ln_bwd", "crf_dgrad_ln_bwd",
-    "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd", "crf_pixel_shuffle_nhwc",
+    "crf_layernorm_fwd", "crf_layernorm_bwd", "crf_layernorm_ps_fwd", "crf_layernorm_ps_bwd", "crf_depth_loss_fwd", "crf_depth_loss_bwd", "crf_pixel_shuffle_nhwc",
     "crf_colsum_bf16", "crf_cast_bf16", "crf_attn_fwd", "crf_attn_bwd", "crf_adam_step",
 )
 
@@ -64,7 +64,7 @@ class BlockGrads(C.Structure):
 
 class LayerArgs(C.Structure):
     _fields_ = [("depth", C.c_int32), ("out_dtype", C.c_int32), ("params", C.POINTER(BlockParams)),
-                ("norm_w", C.c_void_p), ("norm_b", C.c_void_p)]
+                ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("out_shuffle", C.c_int32)]
 
 
 class GemmArgs(C.Structure):
@@ -128,6 +128,8 @@ def _declare(lib):
     lib.crf_dgrad_ln_bwd.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.crf_layernorm_fwd.argtypes = [vp, vp, vp, f32, vp, i32, vp, i32, i32, i32, vp]
     lib.crf_layernorm_bwd.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.crf_layernorm_ps_fwd.argtypes = [vp, vp, vp, f32, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    lib.crf_layernorm_ps_bwd.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.crf_depth_loss_fwd.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp]
     lib.crf_depth_loss_bwd.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, vp, i32, vp]
     lib.crf_pixel_shuffle_nhwc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]

@@ -401,6 +401,8 @@ int check_layer(const crf_block_desc* d, const crf_layer_args* a) {
   CRF_CHECK((a->norm_w == nullptr) == (a->norm_b == nullptr), "crf_layer: norm_w and norm_b go together");
   CRF_CHECK(a->out_dtype == CRF_DT_F32 || (a->out_dtype == CRF_DT_BF16 && a->norm_w != nullptr),
             "crf_layer: bf16 output needs the closing LayerNorm");
+  CRF_CHECK(a->out_shuffle == 0 || (a->out_shuffle == 1 && a->norm_w != nullptr && d->C % 4 == 0),
+            "crf_layer: out_shuffle needs the closing LayerNorm");
   return 0;
 }
 }  // namespace
@@ -439,8 +441,14 @@ int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
     xin = yo;
   }
   if (with_norm) {
-    if (launch_layernorm_fwd(static_cast<const float*>(xin), a->norm_w, a->norm_b, a->params[0].ln_eps, y, a->out_dtype,
-                             reinterpret_cast<float*>(S + L.norm_stats), T, d->C, static_cast<cudaStream_t>(stream)))
+    if (a->out_shuffle) {
+      if (launch_layernorm_ps_fwd(static_cast<const float*>(xin), a->norm_w, a->norm_b, a->params[0].ln_eps, y,
+                                  a->out_dtype, reinterpret_cast<float*>(S + L.norm_stats), d->B, d->H, d->W, d->C,
+                                  static_cast<cudaStream_t>(stream)))
+        return 1;
+    } else if (launch_layernorm_fwd(static_cast<const float*>(xin), a->norm_w, a->norm_b, a->params[0].ln_eps, y,
+                                    a->out_dtype, reinterpret_cast<float*>(S + L.norm_stats), T, d->C,
+                                    static_cast<cudaStream_t>(stream)))
       return 1;
   }
   return 0;
@@ -472,7 +480,12 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
     const float* ylast = reinterpret_cast<const float*>(S + L.yout[a->depth - 1]);
     float* gn = reinterpret_cast<float*>(Wk + W.g_f32);
     // LayerNorm backward writes dx in fp32 and its bf16 twin in one pass (the MLP GEMMs read the twin)
-    if (a->out_dtype == CRF_DT_F32) {
+    if (a->out_shuffle) {
+      if (launch_layernorm_ps_bwd(dy, a->out_dtype, ylast, reinterpret_cast<const float*>(S + L.norm_stats), a->norm_w, gn,
+                                  Wk + W.g_bf16, dnorm_w, dnorm_b, d->B, d->H, d->W, d->C, st))
+        return 1;
+      g16 = Wk + W.g_bf16;
+    } else if (a->out_dtype == CRF_DT_F32) {
       if (launch_ln_bwd(static_cast<const float*>(dy), ylast, reinterpret_cast<const float*>(S + L.norm_stats), a->norm_w,
                         nullptr, gn, Wk + W.g_bf16, dnorm_w, dnorm_b, static_cast<int>(T), d->C, st))
         return 1;
@@ -525,6 +538,23 @@ int crf_shift_mask(float* mask, int H, int W, int window, int shift, void* strea
 
 size_t crf_gemm_workspace_bytes(int M, int N, int K, int device) {
   return gemm_splitk_workspace_bytes(M, N, K, device, nullptr);
+}
+
+int crf_layernorm_ps_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                         float* stats, int B, int H, int W, int C, int device, void* stream) {
+  CRF_CHECK(x && gamma && beta && y && stats && B > 0 && H > 0 && W > 0, "crf_layernorm_ps_fwd: bad arguments");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_layernorm_ps_fwd(x, gamma, beta, eps, y, y_dtype, stats, B, H, W, C, static_cast<cudaStream_t>(stream));
+}
+int crf_layernorm_ps_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                         float* dgamma, float* dbeta, int B, int H, int W, int C, int device, void* stream) {
+  CRF_CHECK(g && x && stats && gamma && dx && dgamma && dbeta && B > 0 && H > 0 && W > 0,
+            "crf_layernorm_ps_bwd: bad arguments");
+  DeviceGuard guard(device);
+  CRF_CHECK(guard.ok, "cannot select device %d", device);
+  return launch_layernorm_ps_bwd(g, g_dtype, x, stats, gamma, dx, nullptr, dgamma, dbeta, B, H, W, C,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int crf_dgrad_ln_bwd(const void* dy_bf16, const void* w_bf16, int K, const float* x, const float* stats,

@@ -99,6 +99,10 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
                          float* stats, int T, int C, cudaStream_t st);
 int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
                          void* dx_bf16, float* dgamma, float* dbeta, int T, int C, cudaStream_t st);
+int launch_layernorm_ps_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                            float* stats, int B, int H, int W, int C, cudaStream_t st);
+int launch_layernorm_ps_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                            void* dx_bf16, float* dgamma, float* dbeta, int B, int H, int W, int C, cudaStream_t st);
 int launch_depth_loss_fwd(const void* pred, int pred_dtype, const float* tgt, int n_img, int H, int W, float* sums,
                           float* G, cudaStream_t st);
 int launch_depth_loss_bwd(const void* pred, int pred_dtype, const float* tgt, const float* G, const float* gout,

@@ -632,6 +632,128 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The closing LayerNorm of a decoder stage with the PixelShuffle(2) that follows it folded into its store / load
+// (model_mobileV3_large_newCRFs.py:116-120: `PixelShuffle(2)` between the stages, fed by newcrf_layers.py:430-432).
+// Token (b, h, w), channel c = 4 k' + 2 i + j  <->  NHWC element (b, 2h + i, 2w + j, k') of the (B, 2H, 2W, C/4) map.
+// Same arithmetic, in the same order, as ln_fwd_rows_kernel / ln_bwd_kernel (one warp per row, lane owns channels
+// {2 lane + 64 k, +1}): a lane's two channels are the j = 0 / 1 neighbours of one output row i = lane & 1.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void store1(T* p, float v);
+template <>
+__device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ float load1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <int NCH, typename TOut>
+__global__ void __launch_bounds__(256)
+layernorm_ps_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float eps, TOut* __restrict__ y, float* __restrict__ stats, int T, int H, int W) {
+  constexpr int C = 64 * NCH, C4 = C / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * 8;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += warps_total) {
+    const float* row = x + static_cast<int64_t>(t) * C;
+    float2 v[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      v[k] = load2(row + 64 * k + 2 * lane);
+      s += v[k].x + v[k].y;
+    }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const float d0 = v[k].x - mean, d1 = v[k].y - mean;
+      q += d0 * d0 + d1 * d1;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    if (lane == 0) {
+      stats[2 * t] = mean;
+      stats[2 * t + 1] = rstd;
+    }
+    const int w = t % W, bh = t / W, h = bh % H, b = bh / H;
+    const int64_t pix = (static_cast<int64_t>(b) * 2 * H + 2 * h + (lane & 1)) * 2 * W + 2 * w;   // (i = lane & 1, j = 0)
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 64 * k + 2 * lane;
+      const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c));
+      const float2 be = __ldg(reinterpret_cast<const float2*>(beta + c));
+      const int kp = 16 * k + (lane >> 1);
+      store1(y + pix * C4 + kp, (v[k].x - mean) * rstd * g.x + be.x);
+      store1(y + (pix + 1) * C4 + kp, (v[k].y - mean) * rstd * g.y + be.y);
+    }
+  }
+}
+
+template <int NCH, typename TG>
+__global__ void __launch_bounds__(256)
+layernorm_ps_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
+                        const float* __restrict__ gamma, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int H, int W) {
+  constexpr int C = 64 * NCH, C4 = C / 4;
+  __shared__ float red[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 gam[NCH], dga[NCH], dbe[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    gam[k] = __ldg(reinterpret_cast<const float2*>(gamma + 64 * k + 2 * lane));
+    dga[k] = make_float2(0.f, 0.f);
+    dbe[k] = make_float2(0.f, 0.f);
+  }
+  const int warps_total = gridDim.x * 8;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += warps_total) {
+    const float mean = __ldg(stats + 2 * t), rstd = __ldg(stats + 2 * t + 1);
+    const float* xr = x + static_cast<int64_t>(t) * C;
+    const int w = t % W, bh = t / W, h = bh % H, b = bh / H;
+    const int64_t pix = (static_cast<int64_t>(b) * 2 * H + 2 * h + (lane & 1)) * 2 * W + 2 * w;
+    float2 gv[NCH], xh[NCH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int kp = 16 * k + (lane >> 1);
+      gv[k] = make_float2(load1(g + pix * C4 + kp), load1(g + (pix + 1) * C4 + kp));
+      const float2 xv = __ldg(reinterpret_cast<const float2*>(xr + 64 * k + 2 * lane));
+      xh[k] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
+      dga[k].x += gv[k].x * xh[k].x; dga[k].y += gv[k].y * xh[k].y;
+      dbe[k].x += gv[k].x;           dbe[k].y += gv[k].y;
+      gv[k].x *= gam[k].x;           gv[k].y *= gam[k].y;
+      s1 += gv[k].x + gv[k].y;
+      s2 += gv[k].x * xh[k].x + gv[k].y * xh[k].y;
+    }
+    s1 = warp_sum(s1) * (1.0f / C);
+    s2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const float o0 = rstd * (gv[k].x - s1 - xh[k].x * s2);
+      const float o1 = rstd * (gv[k].y - s1 - xh[k].y * s2);
+      const int64_t off = static_cast<int64_t>(t) * C + 64 * k + 2 * lane;
+      if (dx != nullptr) *reinterpret_cast<float2*>(dx + off) = make_float2(o0, o1);
+      if (dx_bf16 != nullptr) *reinterpret_cast<uint32_t*>(dx_bf16 + off) = pack_bf16(o0, o1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const float2 v = pass == 0 ? dga[k] : dbe[k];
+      red[warp][2 * lane] = v.x;
+      red[warp][2 * lane + 1] = v.y;
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+        atomicAdd((pass == 0 ? dgamma : dbeta) + 64 * k + threadIdx.x, s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Stand-alone LayerNorm over contiguous (T, C) fp32 rows (the final norm_crf of a decoder stage,
 // newcrf_layers.py:430-431): y fp32 or bf16, stats (mean, rstd) for the backward.
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
@@ -703,6 +825,71 @@ int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float
     default: return set_error("layernorm_bwd: unsupported C=%d", C);
   }
 #undef CRF_LNSB
+  CRF_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+// The closing LayerNorm with the following PixelShuffle(2) folded in: y / g are (B, 2H, 2W, C/4) NHWC maps.
+int launch_layernorm_ps_fwd(const float* x, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                            float* stats, int B, int H, int W, int C, cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "layernorm_ps_fwd: C=%d must be a multiple of 64 in [64,1024]", C);
+  CRF_CHECK(y_dtype == CRF_DT_F32 || y_dtype == CRF_DT_BF16, "layernorm_ps_fwd: unsupported output dtype %d", y_dtype);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int T = B * H * W;
+  int blocks = (T + 7) / 8;
+  const int cap = num_sms(dev) * 8;
+  if (blocks > cap) blocks = cap;
+  KernelTimer tm(st, 0.0, static_cast<double>(T) * C * (4 + (y_dtype == CRF_DT_F32 ? 4 : 2)), "layernorm_ps_fwd_T%d_C%d", T, C);
+#define CRF_LPS(NCH)                                                                                                    \
+  case NCH:                                                                                                             \
+    if (y_dtype == CRF_DT_F32)                                                                                          \
+      layernorm_ps_fwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, reinterpret_cast<float*>(y), stats, \
+                                                                   T, H, W);                                            \
+    else                                                                                                                \
+      layernorm_ps_fwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(x, gamma, beta, eps,                          \
+                                                                           reinterpret_cast<__nv_bfloat16*>(y), stats, T, H, W); \
+    break;
+  switch (C / 64) {
+    CRF_LPS(1) CRF_LPS(2) CRF_LPS(3) CRF_LPS(4) CRF_LPS(5) CRF_LPS(6) CRF_LPS(7) CRF_LPS(8) CRF_LPS(9) CRF_LPS(10)
+    CRF_LPS(11) CRF_LPS(12) CRF_LPS(13) CRF_LPS(14) CRF_LPS(15) CRF_LPS(16)
+    default: return set_error("layernorm_ps_fwd: unsupported C=%d", C);
+  }
+#undef CRF_LPS
+  CRF_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_layernorm_ps_bwd(const void* g, int g_dtype, const float* x, const float* stats, const float* gamma, float* dx,
+                            void* dx_bf16, float* dgamma, float* dbeta, int B, int H, int W, int C, cudaStream_t st) {
+  CRF_CHECK(C % 64 == 0 && C >= 64 && C <= 1024, "layernorm_ps_bwd: C=%d must be a multiple of 64 in [64,1024]", C);
+  CRF_CHECK(g_dtype == CRF_DT_F32 || g_dtype == CRF_DT_BF16, "layernorm_ps_bwd: unsupported gradient dtype %d", g_dtype);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int T = B * H * W;
+  int blocks = (T + 7) / 8;
+  const int cap = num_sms(dev) * (C >= 512 ? 1 : 4);
+  if (blocks > cap) blocks = cap;
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  KernelTimer tm(st, 0.0, static_cast<double>(T) * C * ((g_dtype == CRF_DT_F32 ? 4 : 2) + 8 + (dx_bf16 != nullptr ? 2 : 0)),
+                 "layernorm_ps_bwd_T%d_C%d", T, C);
+#define CRF_LPB(NCH)                                                                                                    \
+  case NCH:                                                                                                             \
+    if (g_dtype == CRF_DT_F32)                                                                                          \
+      layernorm_ps_bwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), x, stats, gamma, dx, \
+                                                                   dxb, dgamma, dbeta, T, H, W);                        \
+    else                                                                                                                \
+      layernorm_ps_bwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), x,  \
+                                                                           stats, gamma, dx, dxb, dgamma, dbeta, T, H, W); \
+    break;
+  switch (C / 64) {
+    CRF_LPB(1) CRF_LPB(2) CRF_LPB(3) CRF_LPB(4) CRF_LPB(5) CRF_LPB(6) CRF_LPB(7) CRF_LPB(8) CRF_LPB(9) CRF_LPB(10)
+    CRF_LPB(11) CRF_LPB(12) CRF_LPB(13) CRF_LPB(14) CRF_LPB(15) CRF_LPB(16)
+    default: return set_error("layernorm_ps_bwd: unsupported C=%d", C);
+  }
+#undef CRF_LPB
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

@@ -165,7 +165,8 @@ class _CRFLayerFn(torch.autograd.Function):
     (crf_layer_fwd / crf_layer_bwd)."""
 
     @staticmethod
-    def forward(ctx, x, v, precision, H, W, num_heads, window, qk_scale, eps, out_bf16, depth, norm_w, norm_b, *params):
+    def forward(ctx, x, v, precision, H, W, num_heads, window, qk_scale, eps, out_bf16, shuffle, depth, norm_w, norm_b,
+                *params):
         B, Ltok, Cd = x.shape
         dev = x.device
         params = tuple(p.detach().contiguous() for p in params)
@@ -181,7 +182,10 @@ class _CRFLayerFn(torch.autograd.Function):
         L.check(L.lib().crf_layer_sizes(C.byref(desc), depth, int(with_norm), C.byref(sb), C.byref(wb)),
                 "crf_layer_sizes")
         saved = _alloc_bytes(sb.value, dev)
-        y = torch.empty(B, Ltok, Cd, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        odt = torch.bfloat16 if out_bf16 else torch.float32
+        # shuffle: the closing LayerNorm stores with the decoder's PixelShuffle(2) folded in -> (B, C/4, 2H, 2W), NHWC memory
+        y = (torch.empty(B, 2 * H, 2 * W, Cd // 4, dtype=odt, device=dev) if shuffle
+             else torch.empty(B, Ltok, Cd, dtype=odt, device=dev))
         pa = (L.BlockParams * depth)()
         for i in range(depth):
             for name, t in zip(L.PARAM_NAMES, params[13 * i:13 * i + 13]):
@@ -190,25 +194,28 @@ class _CRFLayerFn(torch.autograd.Function):
         nw = norm_w.detach().contiguous() if with_norm else None
         nb = norm_b.detach().contiguous() if with_norm else None
         la = L.LayerArgs(depth, L.CRF_DT_BF16 if out_bf16 else L.CRF_DT_F32, pa,
-                         nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None)
+                         nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None, int(bool(shuffle)))
         L.check(L.lib().crf_layer_fwd(C.byref(desc), C.byref(la), xd.data_ptr(), v_arg.data_ptr(), y.data_ptr(),
                                       saved.data_ptr(), _stream_ptr(dev)), "crf_layer_fwd")
         _check_guard(saved, sb.value, "crf_layer_fwd saved")
         if training:
             ctx.save_for_backward(xd, v_arg, saved, *((nw, nb) if with_norm else ()), *params)
             ctx.desc = desc
-            ctx.meta = (H, W, qk_scale, eps, out_bf16, depth, with_norm, wb.value)
-        return y
+            ctx.meta = (H, W, qk_scale, eps, out_bf16, depth, with_norm, wb.value, bool(shuffle))
+        return y.permute(0, 3, 1, 2) if shuffle else y
 
     @staticmethod
     def backward(ctx, dy):
-        H, W, qk_scale, eps, out_bf16, depth, with_norm, ws_bytes = ctx.meta
+        H, W, qk_scale, eps, out_bf16, depth, with_norm, ws_bytes, shuffle = ctx.meta
         xd, v_arg, saved, *rest = ctx.saved_tensors
         nw, nb = (rest[0], rest[1]) if with_norm else (None, None)
         params = rest[2:] if with_norm else rest
         desc, dev = ctx.desc, xd.device
         B, Ltok, Cd = xd.shape
-        dy = dy.contiguous().to(torch.bfloat16 if out_bf16 else torch.float32)
+        if shuffle:   # (B, C/4, 2H, 2W) gradient -> NHWC memory, the layout the fused LayerNorm backward reads
+            dy = dy.to(torch.bfloat16 if out_bf16 else torch.float32).contiguous(memory_format=torch.channels_last)
+        else:
+            dy = dy.contiguous().to(torch.bfloat16 if out_bf16 else torch.float32)
         ws = _alloc_bytes(ws_bytes, dev)
         dx = torch.empty(B, Ltok, Cd, dtype=xd.dtype, device=dev)   # in x's dtype: no autograd cast afterwards
         dv = torch.empty(B, H, W, Cd, dtype=torch.float32, device=dev)
@@ -227,7 +234,7 @@ class _CRFLayerFn(torch.autograd.Function):
                 setattr(ga[i], name, views[13 * i + k].data_ptr())
             pa[i].qk_scale, pa[i].ln_eps = float(qk_scale), float(eps)
         la = L.LayerArgs(depth, L.CRF_DT_BF16 if out_bf16 else L.CRF_DT_F32, pa,
-                         nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None)
+                         nw.data_ptr() if with_norm else None, nb.data_ptr() if with_norm else None, int(shuffle))
         dnw = views[13 * depth].data_ptr() if with_norm else None
         dnb = views[13 * depth + 1].data_ptr() if with_norm else None
         L.check(L.lib().crf_layer_bwd(C.byref(desc), C.byref(la), xd.data_ptr(), v_arg.data_ptr(), dy.data_ptr(),
@@ -235,14 +242,16 @@ class _CRFLayerFn(torch.autograd.Function):
                                       ws_bytes, _stream_ptr(dev)), "crf_layer_bwd")
         _check_guard(ws, ws_bytes, "crf_layer_bwd workspace")
         gn = (views[13 * depth], views[13 * depth + 1]) if with_norm else (None, None)
-        return (dx, dv, None, None, None, None, None, None, None, None, None, gn[0], gn[1], *views[:13 * depth])
+        return (dx, dv, None, None, None, None, None, None, None, None, None, None, gn[0], gn[1], *views[:13 * depth])
 
 
 def crf_layer(x, v, H, W, block_params, num_heads, *, window=7, qk_scale=None, eps=1e-5, norm=None, out_dtype=None,
-              precision=None):
+              precision=None, pixel_shuffle=False):
     """BasicCRFLayer.forward as one call: block_params = [13 tensors in PARAM_KEYS order] per block (shift 0,
     window // 2, 0, ...); norm = (weight, bias) of a closing LayerNorm or None; out_dtype torch.bfloat16 only with
-    norm.  Returns (B, H*W, C).  Mirrors the reference's error behaviour (newcrf_layers.py:205,143)."""
+    norm.  Returns (B, H*W, C) -- or, with pixel_shuffle=True (needs norm), F.pixel_shuffle(y as NCHW, 2): a
+    (B, C/4, 2H, 2W) channels-last tensor written directly by the closing LayerNorm
+    (model_mobileV3_large_newCRFs.py:116-120).  Mirrors the reference's error behaviour (newcrf_layers.py:205,143)."""
     assert x.dim() == 3 and v.dim() == 4
     B, Ltok, Cd = x.shape
     assert Ltok == H * W, "input feature has wrong size"
@@ -259,8 +268,9 @@ def crf_layer(x, v, H, W, block_params, num_heads, *, window=7, qk_scale=None, e
     nw, nb = norm if norm is not None else (None, None)
     out_bf16 = out_dtype == torch.bfloat16
     assert not out_bf16 or norm is not None, "bf16 output needs the closing LayerNorm"
+    assert not pixel_shuffle or (norm is not None and Cd % 4 == 0), "pixel_shuffle needs the closing LayerNorm"
     return _CRFLayerFn.apply(x, v, _precision_code(precision), H, W, num_heads, window, float(qk_scale), float(eps),
-                             out_bf16, len(block_params), nw, nb, *flat)
+                             out_bf16, bool(pixel_shuffle), len(block_params), nw, nb, *flat)
 
 
 class _LayerNormFn(torch.autograd.Function):

@@ -178,8 +178,9 @@ class BasicCRFLayer(nn.Module):
                         and b.window_size == self.window_size and b.norm1.eps == blk0.norm1.eps
                         and b.attn.scale == blk0.attn.scale for i, b in enumerate(self.blocks)))
 
-    def run(self, x, v, H, W, norm=None, out_dtype=None):
-        """The layer, optionally closed by `norm` (an nn.LayerNorm: NewCRF.norm_crf) -> (B, H*W, C)."""
+    def run(self, x, v, H, W, norm=None, out_dtype=None, pixel_shuffle=False):
+        """The layer, optionally closed by `norm` (an nn.LayerNorm: NewCRF.norm_crf) -> (B, H*W, C); with
+        pixel_shuffle=True (fused path only, needs norm) -> F.pixel_shuffle of the NCHW result, (B, C/4, 2H, 2W)."""
         for blk in self.blocks:
             blk.H, blk.W = H, W
         if self._fusable(x) and (norm is None or (type(norm) is nn.LayerNorm and norm.elementwise_affine
@@ -189,7 +190,7 @@ class BasicCRFLayer(nn.Module):
             return CF.crf_layer(x, v, H, W, [b.fused_params() for b in self.blocks], blk0.num_heads,
                                 window=self.window_size, qk_scale=blk0.attn.scale, eps=blk0.norm1.eps,
                                 norm=None if norm is None else (norm.weight, norm.bias), out_dtype=out_dtype,
-                                precision=self.precision)
+                                precision=self.precision, pixel_shuffle=pixel_shuffle)
         v_bf16 = CF.convert_v(v) if (v.is_cuda and self.depth > 1) else None  # both blocks read the same v
         for blk in self.blocks:
             if blk.precision is None:
@@ -197,6 +198,9 @@ class BasicCRFLayer(nn.Module):
             x = blk(x, v, None, v_bf16=v_bf16)
         if norm is not None:
             x = norm(x)
+        if pixel_shuffle:
+            B, _, Cd = x.shape
+            x = F.pixel_shuffle(x.view(B, H, W, Cd).permute(0, 3, 1, 2), 2)
         return x
 
     def forward(self, x, v, H, W):
@@ -253,7 +257,9 @@ class NewCRF(nn.Module):
                                        use_checkpoint=False)
         self.norm_crf = norm_layer(embed_dim)
 
-    def forward(self, x, v):
+    def forward(self, x, v, pixel_shuffle=False):
+        """pixel_shuffle=True returns nn.PixelShuffle(2) of the stage's output (the decoder applies it to three of the
+        four stages, model_mobileV3_large_newCRFs.py:116-120): the closing LayerNorm then writes the shuffled map itself."""
         if self.proj_x is not None:
             x = _project(self.proj_x, x)
         if self.proj_v is not None:
@@ -265,7 +271,9 @@ class NewCRF(nn.Module):
         # next consumer is a convolution that would cast the fp32 result anyway -- same values, one pass less)
         bf16 = x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
         y = self.crf_layer.run(tokens, v_hwc, Wh, Ww, norm=self.norm_crf,
-                               out_dtype=torch.bfloat16 if bf16 else torch.float32)
+                               out_dtype=torch.bfloat16 if bf16 else torch.float32, pixel_shuffle=pixel_shuffle)
+        if pixel_shuffle:
+            return y   # (B, C/4, 2H, 2W), channels-last memory
         out = y.view(B, Wh, Ww, self.embed_dim).permute(0, 3, 1, 2)
         if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
             return out  # channels-last pipeline: the token-major result already IS NHWC memory, no copy needed

@@ -84,6 +84,46 @@ def test_layer_matches_reference_golden(name):
     assert not bad, f"rel_l2 above the bound: {bad}\nall: {errs}"
 
 
+@pytest.mark.parametrize("out_bf16", [False, True])
+@pytest.mark.parametrize("B,H,W,C,nH,depth", [(2, 9, 10, 64, 2, 2), (2, 15, 20, 128, 4, 2), (1, 30, 40, 256, 8, 1)])
+def test_layer_with_pixel_shuffle_folded_in(B, H, W, C, nH, depth, out_bf16):
+    """crf_layer_args.out_shuffle: the stage-closing LayerNorm writes nn.PixelShuffle(2) of the stage's NCHW output
+    (model_mobileV3_large_newCRFs.py:116-120) -- bit-identical to the unshuffled layer call + F.pixel_shuffle, and the
+    same gradients (the backward reads the shuffled gradient map)."""
+    pkg = _pkg()
+    torch.manual_seed(11 * depth + C)
+    layer = pkg.BasicCRFLayer(dim=C, depth=depth, num_heads=nH, v_dim=C).to(DEV)
+    norm = torch.nn.LayerNorm(C).to(DEV)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.2)
+        norm.bias.normal_(0.0, 0.2)
+    x0 = torch.randn(B, C, H, W, device=DEV).flatten(2).transpose(1, 2)
+    v0 = torch.randn(B, C, H, W, device=DEV).permute(0, 2, 3, 1)
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    gy = torch.randn(B, C // 4, 2 * H, 2 * W, device=DEV).to(odt)
+
+    def run(shuffle):
+        for p_ in list(layer.parameters()) + list(norm.parameters()):
+            p_.grad = None
+        x, v = x0.detach().requires_grad_(True), v0.detach().requires_grad_(True)
+        y = layer.run(x, v, H, W, norm=norm, out_dtype=odt, pixel_shuffle=shuffle)
+        if not shuffle:
+            y = torch.nn.functional.pixel_shuffle(y.view(B, H, W, C).permute(0, 3, 1, 2), 2)
+        assert y.shape == (B, C // 4, 2 * H, 2 * W)
+        y.backward(gy)
+        grads = {k: p_.grad.clone() for k, p_ in layer.named_parameters()}
+        grads.update({"norm." + k: p_.grad.clone() for k, p_ in norm.named_parameters()})
+        return y.detach(), x.grad.clone(), v.grad.clone(), grads
+
+    yf, dxf, dvf, gf = run(True)
+    yr, dxr, dvr, gr = run(False)
+    assert yf.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(yf, yr), "forward differs"
+    assert rel_l2(dxf, dxr) < 1e-6 and rel_l2(dvf, dvr) < 1e-6, (rel_l2(dxf, dxr), rel_l2(dvf, dvr))
+    bad = {k: rel_l2(gf[k], gr[k]) for k in gr if not rel_l2(gf[k], gr[k]) < 1e-5}
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("with_norm,out_bf16", [(False, False), (True, False), (True, True)])
 @pytest.mark.parametrize("B,H,W,C,nH,depth", [(2, 9, 10, 64, 2, 2), (2, 15, 20, 128, 4, 3), (1, 30, 40, 256, 8, 1)])
 def test_layer_call_equals_block_by_block(B, H, W, C, nH, depth, with_norm, out_bf16):

@@ -498,6 +498,55 @@ def test_depth_loss_matches_reference_golden():
                2e-4, f"depth_loss d pred ({tag})")
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 5, 7, 64), (2, 15, 20, 1024), (8, 30, 40, 512), (3, 9, 11, 256), (1, 1, 1, 128)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_pixel_shuffle_fused(B, H, W, C, dtype):
+    """The closing LayerNorm of a decoder stage with the following nn.PixelShuffle(2) folded into its store / load
+    (crf_layernorm_ps_fwd / _bwd; model_mobileV3_large_newCRFs.py:116-120): bit-identical to LayerNorm kernel +
+    F.pixel_shuffle, forward and backward."""
+    import ctypes as Cc
+    L = _L()
+    lib = L.lib()
+    g = torch.Generator(device="cpu").manual_seed(B * H * W + C)
+    T = B * H * W
+    x = (torch.randn(T, C, generator=g) * 1.3 + 0.2).to(DEV)
+    gam = (1.0 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    bet = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    st = Cc.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dt = L.CRF_DT_BF16 if dtype == torch.bfloat16 else L.CRF_DT_F32
+    # forward
+    y_ps = torch.full((B, 2 * H, 2 * W, C // 4), float("nan"), dtype=dtype, device=DEV)
+    stats = torch.empty(T, 2, device=DEV)
+    L.check(lib.crf_layernorm_ps_fwd(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-5, y_ps.data_ptr(), dt,
+                                     stats.data_ptr(), B, H, W, C, 0, st), "crf_layernorm_ps_fwd")
+    y = torch.empty(T, C, dtype=dtype, device=DEV)
+    stats2 = torch.empty(T, 2, device=DEV)
+    L.check(lib.crf_layernorm_fwd(x.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-5, y.data_ptr(), dt, stats2.data_ptr(),
+                                  T, C, 0, st), "crf_layernorm_fwd")
+    torch.cuda.synchronize()
+    ref = F.pixel_shuffle(y.view(B, H, W, C).permute(0, 3, 1, 2), 2)          # (B, C/4, 2H, 2W)
+    assert torch.equal(y_ps.permute(0, 3, 1, 2), ref)
+    assert torch.equal(stats, stats2)
+    _check(y_ps.permute(0, 3, 1, 2).float(), F.pixel_shuffle(
+        F.layer_norm(x, (C,), gam, bet, 1e-5).view(B, H, W, C).permute(0, 3, 1, 2), 2), 4e-3 if dtype == torch.bfloat16 else 1e-5,
+        "layernorm_ps.y")
+    # backward
+    gy = torch.randn(B, 2 * H, 2 * W, C // 4, generator=g).to(DEV).to(dtype)        # NHWC gradient of the shuffled map
+    dx = torch.full((T, C), float("nan"), device=DEV)
+    dgam, dbet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    L.check(lib.crf_layernorm_ps_bwd(gy.data_ptr(), dt, x.data_ptr(), stats.data_ptr(), gam.data_ptr(), dx.data_ptr(),
+                                     dgam.data_ptr(), dbet.data_ptr(), B, H, W, C, 0, st), "crf_layernorm_ps_bwd")
+    g_tok = F.pixel_unshuffle(gy.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).reshape(T, C).contiguous()
+    dx2 = torch.empty(T, C, device=DEV)
+    dgam2, dbet2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    L.check(lib.crf_layernorm_bwd(g_tok.data_ptr(), dt, x.data_ptr(), stats.data_ptr(), gam.data_ptr(), dx2.data_ptr(),
+                                  dgam2.data_ptr(), dbet2.data_ptr(), T, C, 0, st), "crf_layernorm_bwd")
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx2)
+    _check(dgam, dgam2, 1e-5, "layernorm_ps.dgamma")
+    _check(dbet, dbet2, 1e-5, "layernorm_ps.dbeta")
+
+
 def test_colsum_cast_convert():
     ops = _ops()
     for T_, N_ in ((1234, 384), (7, 8), (153600, 128), (38400, 256), (9600, 512), (2401, 1024), (333, 4096)):
