@@ -82,6 +82,7 @@ struct MlpArgs {
   int T;
   int training;        // 1: xn2 / pre / act are stored for the backward pass
   int prof;            // debug timeline on
+  int tm;              // token rows per tile actually loaded / stored (<= 128, multiple of 8): see launch_mlp_c
 };
 
 template <int C>
@@ -116,7 +117,8 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   float* bias_s = reinterpret_cast<float*>(gen + PL::kBiasOff);  // b1[0 .. 4C), b2, gamma, beta [0 .. C) each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = (a.T + TM - 1) / TM;
+  const int tm = a.tm;
+  const int total_tiles = (a.T + tm - 1) / tm;
   const int my_tiles =
       (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const uint32_t n_chunks = static_cast<uint32_t>(my_tiles) * NJ;  // global chunk index g = tile * NJ + j
@@ -276,7 +278,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     const float* gamma_s = bias_s + 5 * C;
     const float* beta_s = bias_s + 6 * C;
     for (int i = 0; i < my_tiles; ++i) {
-      const int t0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TM;
+      const int t0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * tm;
       const int xb = i % kXnBufs;
       if (tid == 0) {
         if (i >= kXnBufs) mbar_wait_sleep(xn_empty + 8u * xb, ((i / kXnBufs) - 1) & 1);  // fc1 of tile i-kXnBufs has read it
@@ -290,8 +292,8 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
         float4 v[SB][NV];
 #pragma unroll
         for (int q = 0; q < SB; ++q) {
-          const int t = t0 + 16 * warp + 4 * (st0 + q) + rq;
-          const int tc = t < a.T ? t : a.T - 1;  // tail rows re-read the last row (zeroed below, never stored)
+          const int rr = 16 * warp + 4 * (st0 + q) + rq, t = t0 + rr;
+          const int tc = (rr < tm && t < a.T) ? t : t0;  // rows past the tile / the input re-read row t0 (zeroed below, never stored)
           const float4* row = reinterpret_cast<const float4*>(a.x1 + static_cast<size_t>(tc) * C) + sub;
 #pragma unroll
           for (int k = 0; k < NV; ++k) v[q][k] = __ldg(row + 8 * k);
@@ -316,7 +318,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
           d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
           d2 += __shfl_xor_sync(0xffffffffu, d2, 4);
           const float rstd = rsqrtf(d2 * (1.0f / C) + a.eps);
-          const bool live = t < a.T;
+          const bool live = r < tm && t < a.T;   // rows >= tm of the 128-row MMA tile belong to the next tile: zero, never stored
           if (live && sub == 0 && a.stats != nullptr)
             *reinterpret_cast<float2*>(a.stats + 2 * static_cast<size_t>(t)) = make_float2(mean, rstd);
 #pragma unroll
@@ -359,7 +361,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll 1
     for (uint32_t g = gi; g < n_chunks; g += 2) {
       const int i = static_cast<int>(g / NJ), j = static_cast<int>(g % NJ);
-      const int t0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TM;
+      const int t0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * tm;
       const uint32_t pb = g % kPreBufs;
       mbar_wait(pre_full + 8u * pb, (g / kPreBufs) & 1);
       tc_fence_after();
@@ -426,9 +428,9 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     uint8_t* outb = gen + PL::kOutOff;
     const float* b2_s = bias_s + 4 * C;
     for (int i = 0; i < my_tiles; ++i) {
-      const int t0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TM;
+      const int t0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * tm;
       const int yb = i % kYBufs;
-      const int t = t0 + r < a.T ? t0 + r : a.T - 1;  // rows beyond T: clipped by the TMA store
+      const int t = (r < tm && t0 + r < a.T) ? t0 + r : t0;  // rows past the tile / the input: not stored (TMA box = tm rows)
       const float4* xrow = reinterpret_cast<const float4*>(a.x1 + static_cast<size_t>(t) * C);
       float4 xr[8];
 #pragma unroll
@@ -488,23 +490,37 @@ int launch_mlp_c(const crf_mlp_args& m, cudaStream_t st) {
   CUtensorMap tmW1, tmW2, tmY, tmXn, tmPre, tmAct;
   if (make_tmap_bf16(&tmW1, m.w1_bf16, 4 * C, C, HC)) return 1;
   if (make_tmap_bf16(&tmW2, m.w2_bf16, C, 4 * C, 128)) return 1;
-  if (make_tmap_f32(&tmY, m.y, m.T, C, TM)) return 1;
+  // Rows per tile: the MMA tile is always 128 rows; only `tm` of them are normalised, multiplied for real and stored, with
+  // tm chosen so that the tiles fill whole rounds of the persistent grid (T = 38400: 300 tiles of 128 rows = 2.03 rounds
+  // on 148 SMs, i.e. 3 rounds; 437 tiles of 88 rows = 2.95 rounds of a shorter tile).  CRF_MLP_TM128=1: always 128.
+  const int sms = num_sms(m.device);
+  int tm = TM;
+  {
+    const int g0 = (m.T + TM - 1) / TM < sms ? (m.T + TM - 1) / TM : sms;
+    const int rows_per_cta = (m.T + g0 - 1) / g0;
+    const int n = (rows_per_cta + TM - 1) / TM;
+    tm = (((rows_per_cta + n - 1) / n) + 7) & ~7;
+    if (tm > TM) tm = TM;
+    static const bool fixed = getenv("CRF_MLP_TM128") != nullptr;
+    if (fixed) tm = TM;
+  }
+  if (make_tmap_f32(&tmY, m.y, m.T, C, tm)) return 1;
   if (m.training) {
-    if (make_tmap_bf16(&tmXn, m.xn2, m.T, C, TM)) return 1;
-    if (make_tmap_bf16(&tmPre, m.pre, m.T, 4 * C, TM)) return 1;
-    if (make_tmap_bf16(&tmAct, m.act, m.T, 4 * C, TM)) return 1;
+    if (make_tmap_bf16(&tmXn, m.xn2, m.T, C, tm)) return 1;
+    if (make_tmap_bf16(&tmPre, m.pre, m.T, 4 * C, tm)) return 1;
+    if (make_tmap_bf16(&tmAct, m.act, m.T, 4 * C, tm)) return 1;
   } else {
     tmXn = tmW1; tmPre = tmW1; tmAct = tmW1;
   }
   auto kern = mlp_fused_fwd_kernel<C>;
   CRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PL::kSmemBytes));
-  const int tiles = (m.T + TM - 1) / TM;
-  int grid = num_sms(m.device);
+  const int tiles = (m.T + tm - 1) / tm;
+  int grid = sms;
   if (grid > tiles) grid = tiles;
   static const int prof = [] { const char* e = getenv("CRF_MLP_PROF"); return e != nullptr && e[0] == '1' ? 1 : 0; }();
-  MlpArgs a{m.x1, m.norm_w, m.norm_b, m.b1, m.b2, m.training ? m.stats : nullptr, m.eps, m.T, m.training ? 1 : 0, prof};
+  MlpArgs a{m.x1, m.norm_w, m.norm_b, m.b1, m.b2, m.training ? m.stats : nullptr, m.eps, m.T, m.training ? 1 : 0, prof, tm};
   const double tc = static_cast<double>(m.T) * C;
-  KernelTimer tm(st, 16.0 * tc * C, tc * (8.0 + (m.training ? 18.0 : 0.0)) + 16.0 * C * C, "mlp_fused_fwd_T%d_C%d%s",
+  KernelTimer timer(st, 16.0 * tc * C, tc * (8.0 + (m.training ? 18.0 : 0.0)) + 16.0 * C * C, "mlp_fused_fwd_T%d_C%d%s",
                  m.T, C, m.training ? "" : "_infer");
   kern<<<grid, kThreads, PL::kSmemBytes, st>>>(tmW1, tmW2, tmY, tmXn, tmPre, tmAct, a);
   CRF_CUDA(cudaGetLastError());
