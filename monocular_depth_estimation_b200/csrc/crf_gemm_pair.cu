@@ -342,8 +342,8 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   // Stream-K (see the kernel) runs when the caller hands over the partial-tile workspace (gemm_pair_streamk_bytes) and
   // a pair's share is at least a quarter of a tile's K loop (<= 5 contributors per tile).  MEASURED on B200 (round 2,
   // profiles/r02_gemm_streamk.md): bit-stable and correct, but NOT faster -- with all 74 pairs busy the time per K chunk
-  // doubles (0.45 -> 0.8 us): these GEMMs are bound by the L2 -> SM operand traffic (tiles x K chunks x 64 KB at
-  // ~5.5-6 TB/s), not by how the tiles pack into rounds.  So the block orchestration passes the workspace only with
+  // doubles (0.45 -> 0.8 us): these GEMMs are bound by a chip-wide resource on the operand path (tiles x K chunks x 64 KB
+  // of TMA fills at ~5 TB/s either way), not by how the tiles pack into rounds.  So the block orchestration passes the workspace only with
   // CRF_GEMM_STREAMK=1; through the C ABI (crf_gemm) the workspace itself is the switch.
   int streamk = 0, snap = 1;
   float* sk_ws = nullptr;
