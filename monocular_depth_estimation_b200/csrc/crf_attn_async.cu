@@ -303,6 +303,7 @@ __device__ __forceinline__ void warp_store_rows64(uint8_t* scratch, int lane, co
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_async_kernel(const AttnParams P) {
+  pdl_launch_dependents();   // (the relative-position table below is a parameter: read before pdl_wait)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -330,6 +331,7 @@ attn_fwd_async_kernel(const AttnParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_ptr_gen;
 
   if (warp >= 12) {
@@ -496,6 +498,7 @@ attn_fwd_async_kernel(const AttnParams P) {
 // =====================================================================================================
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_async_kernel(const AttnParams P) {
+  pdl_launch_dependents();   // (the relative-position table below is a parameter: read before pdl_wait)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -523,6 +526,7 @@ attn_bwd_async_kernel(const AttnParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_ptr_gen;
 
   if (warp >= 12) {
@@ -796,7 +800,7 @@ int launch_attn_fwd_async(const AttnParams& P, const crf_block_desc& d, cudaStre
   const double TC = static_cast<double>(d.B) * d.H * d.W * d.C;
   KernelTimer tm(st, 4.0 * 49 * 49 * d.C * P.total_windows, 8.0 * TC, "attn_fwd_B%d_%dx%d_C%d_s%d", d.B, d.H, d.W, d.C,
                  d.shift);
-  attn_fwd_async_kernel<<<dim3(grid_x(P, d), P.nH), kThreads, smem, st>>>(P);
+  launch_pdl(attn_fwd_async_kernel, dim3(grid_x(P, d), P.nH), kThreads, smem, st, P);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;
@@ -808,7 +812,7 @@ int launch_attn_bwd_async(const AttnParams& P, const crf_block_desc& d, cudaStre
   const double TC = static_cast<double>(d.B) * d.H * d.W * d.C;
   KernelTimer tm(st, 10.0 * 49 * 49 * d.C * P.total_windows, 16.0 * TC, "attn_bwd_B%d_%dx%d_C%d_s%d", d.B, d.H, d.W,
                  d.C, d.shift);
-  attn_bwd_async_kernel<<<dim3(grid_x(P, d), P.nH), kThreads, smem, st>>>(P);
+  launch_pdl(attn_bwd_async_kernel, dim3(grid_x(P, d), P.nH), kThreads, smem, st, P);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

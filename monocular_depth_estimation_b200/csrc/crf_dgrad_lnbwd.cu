@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 dgrad_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
                    const __grid_constant__ CUtensorMap tmDx, const __grid_constant__ CUtensorMap tmDxb, const LnArgs a) {
+  pdl_launch_dependents();
   using PL = LnPlan<C>;
   constexpr int kAcc = PL::kAcc, NS = C / 32;
   const int kStages = a.n_ring, kSlabStages = a.n_slab;
@@ -134,6 +135,7 @@ dgrad_lnbwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 8) {
@@ -417,7 +419,7 @@ int launch_c(const void* dY, const void* W, int K, const float* x, const float* 
   KernelTimer timer(st, 2.0 * tc * K,
                  2.0 * T * K + 2.0 * K * C + tc * (4.0 + (dres ? 4.0 : 0.0) + (dx ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0)),
                  "dgrad_lnbwd_T%d_C%d_K%d", T, C, K);
-  kern<<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, tmX, tmRes, tmDx, tmDxb, a);
+  launch_pdl(kern, grid, kThreads, smem_bytes, st, tmA, tmB, tmX, tmRes, tmDx, tmDxb, a);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

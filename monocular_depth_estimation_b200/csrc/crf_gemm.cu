@@ -44,6 +44,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
             const __grid_constant__ CUtensorMap tmAux, int M, int N, int total_chunks, int chunks_per_split, int stages,
             int a_major, int b_major, EpiParams ep, int chunks_per_part, int a_off, int b_off) {
+  pdl_prologue();
   // chunks_per_part > 0: split-operand mode (crf_gemm_args.split3).  Both operands are stored as [hi | lo] halves side
   // by side and the K loop runs three times: chunk kc belongs to part kc / chunks_per_part = 0: hi*hi, 1: hi*lo(B),
   // 2: lo(A)*hi; the lo half of an operand is a_off / b_off elements further along its contiguous dimension.
@@ -240,6 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // dW[m,n] += sum_z part[z][m][n]
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int M, int N, int m_pad, int splits) {
+  pdl_prologue();
   const int64_t i4 = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   const int64_t total4 = static_cast<int64_t>(M) * N / 4;
   if (i4 >= total4) return;
@@ -289,7 +291,7 @@ int launch_one(const Launch& L, const crf_gemm_args& a, cudaStream_t st) {
   KernelTimer tm(st, 2.0 * mn * a.K, (a.split3 ? 2.0 : 1.0) * 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
                  "gemm%s_%s_epi%d_M%d_N%d_K%d", a.split3 ? "3" : "", a.a_major ? "wgrad" : (a.b_major ? "dgrad" : "fprop"), EPI,
                  a.M, a.N, a.K);
-  kern<<<grid, kThreads, smem, st>>>(L.tmA, L.tmB, L.tmO0, L.tmO1, L.tmAux, a.M, a.N, L.total_chunks, L.cps, stages,
+  launch_pdl(kern, grid, kThreads, smem, st, L.tmA, L.tmB, L.tmO0, L.tmO1, L.tmAux, a.M, a.N, L.total_chunks, L.cps, stages,
                                      a.a_major, a.b_major, ep, L.chunks_per_part, L.a_off, L.b_off);
   CRF_CUDA(cudaGetLastError());
   note_launch();
@@ -423,7 +425,7 @@ int launch_gemm(const crf_gemm_args& a, cudaStream_t st) {
     if (launch_bn_dispatch(BN, L, b, epi, st)) return 1;
     const int64_t total4 = static_cast<int64_t>(a.M) * a.N / 4;
     KernelTimer tm(st, 0.0, 4.0 * a.M * a.N * (L.splits + 2), "splitk_reduce_M%d_N%d_S%d", a.M, a.N, L.splits);
-    splitk_reduce_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
+    launch_pdl(splitk_reduce_kernel, static_cast<unsigned>((total4 + 255) / 256), 256, 0, st, 
         reinterpret_cast<const float*>(a.workspace), reinterpret_cast<float*>(a.out0), a.M, a.N, L.m_pad, L.splits);
     CRF_CUDA(cudaGetLastError());
     note_launch();

@@ -95,6 +95,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                  const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep, int streamk,
                  int snap, float* sk_ws, uint32_t* sk_flags) {
+  pdl_launch_dependents();
   using TR = EpiTraits<EPI>;
   constexpr int kSlabCols = TR::kSlabCols;
   constexpr int kNumSlabs = 128 / kSlabCols;   // per epilogue group (128 of the 256 columns)
@@ -142,6 +143,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs are initialised before anything signals across the pair
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 8) {
@@ -372,13 +374,15 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see launch_pdl (crf_host.h)
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   CRF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep, streamk, snap,
                                 sk_ws, sk_flags));
   note_launch();

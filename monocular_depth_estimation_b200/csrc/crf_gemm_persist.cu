@@ -46,6 +46,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const __grid_constant__ CUtensorMap tmAux, int M, int N, int K, int b_major, EpiParams ep,
                        int splits) {
+  pdl_launch_dependents();
   // splits > 1 (fp32-output epilogues only): every output tile is computed by `splits` work units, each over a
   // contiguous range of K chunks, and every unit ADDS its fp32 tile into the (zero-filled) output with a TMA reduction;
   // unit 0 of a tile also adds the bias / residual.  Used where the tile count quantises badly on the SM count
@@ -101,6 +102,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 16) {
@@ -262,7 +264,7 @@ int launch_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
                            : 4 * mn;
   KernelTimer tm(st, 2.0 * mn * a.K, 2.0 * (static_cast<double>(a.M) + a.N) * a.K + out_bytes,
                  "gemm_%s_epi%d_M%d_N%d_K%d", a.b_major ? "dgrad" : "fprop", EPI, a.M, a.N, a.K);
-  kern<<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep, splits);
+  launch_pdl(kern, grid, kThreads, kSmemBytes, st, tmA, tmB, tmO0, tmO1, tmAux, a.M, a.N, a.K, a.b_major, ep, splits);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

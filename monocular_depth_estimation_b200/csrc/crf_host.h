@@ -68,6 +68,25 @@ void timing_enable(bool on);
 size_t timing_report(char* buf, size_t cap);   // kernel-launch counter exported as crf_kernel_launches()
 long long launch_count();
 
+// Kernel launch with the programmatic-stream-serialization attribute (PDL): the kernel may be scheduled while the
+// previous kernel of the stream is still draining; every kernel launched through here begins with pdl_prologue()
+// (crf_ptx.cuh), which waits for the previous grid before anything else runs.  CRF_PDL=0 launches without the attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- internal launchers (stream-ordered, no allocation) ----
 int launch_gemm(const crf_gemm_args& a, cudaStream_t st);
 int launch_gemm_persistent(const crf_gemm_args& a, cudaStream_t st);  // -1: shape not eligible

@@ -31,6 +31,7 @@ template <typename TP>
 __global__ void __launch_bounds__(256)
 loss_fwd_kernel(const TP* __restrict__ pred, const float* __restrict__ tgt, int H, int W, float* __restrict__ sums,
                 float* __restrict__ G, int64_t plane_stride_g) {
+  pdl_prologue();
   const int w = blockIdx.x * 32 + threadIdx.x;
   const int64_t img = static_cast<int64_t>(blockIdx.z) * H * W;
   float v_ssim = 0.f, v_l1 = 0.f;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(256)
 loss_bwd_kernel(const TP* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ G,
                 int64_t plane_stride_g, const float* __restrict__ gout, int H, int W, float inv_n,
                 TP* __restrict__ dpred) {
+  pdl_prologue();
   const int w = blockIdx.x * 32 + threadIdx.x, h = blockIdx.y * 8 + threadIdx.y;
   if (h >= H || w >= W) return;
   const int64_t img = static_cast<int64_t>(blockIdx.z) * H * W;
@@ -136,9 +138,9 @@ int launch_depth_loss_fwd(const void* pred, int pred_dtype, const float* tgt, in
   const int64_t plane = static_cast<int64_t>(n_img) * H * W;
   KernelTimer tm(st, 0.0, static_cast<double>(plane) * (8 + (G != nullptr ? 12 : 0)), "depth_loss_fwd_%dx%dx%d", n_img, H, W);
   if (pred_dtype == CRF_DT_F32)
-    loss_fwd_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(pred), tgt, H, W, sums, G, plane);
+    launch_pdl((loss_fwd_kernel<float>), grid, block, 0, st, reinterpret_cast<const float*>(pred), tgt, H, W, sums, G, plane);
   else
-    loss_fwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(pred), tgt, H, W, sums,
+    launch_pdl((loss_fwd_kernel<__nv_bfloat16>), grid, block, 0, st, reinterpret_cast<const __nv_bfloat16*>(pred), tgt, H, W, sums,
                                                            G, plane);
   CRF_CUDA(cudaGetLastError());
   note_launch();
@@ -154,10 +156,10 @@ int launch_depth_loss_bwd(const void* pred, int pred_dtype, const float* tgt, co
   const float inv_n = 1.0f / static_cast<float>(plane);
   KernelTimer tm(st, 0.0, static_cast<double>(plane) * 24, "depth_loss_bwd_%dx%dx%d", n_img, H, W);
   if (pred_dtype == CRF_DT_F32)
-    loss_bwd_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(pred), tgt, G, plane, gout, H, W, inv_n,
+    launch_pdl((loss_bwd_kernel<float>), grid, block, 0, st, reinterpret_cast<const float*>(pred), tgt, G, plane, gout, H, W, inv_n,
                                                    reinterpret_cast<float*>(dpred));
   else
-    loss_bwd_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(pred), tgt, G, plane,
+    launch_pdl((loss_bwd_kernel<__nv_bfloat16>), grid, block, 0, st, reinterpret_cast<const __nv_bfloat16*>(pred), tgt, G, plane,
                                                            gout, H, W, inv_n, reinterpret_cast<__nv_bfloat16*>(dpred));
   CRF_CUDA(cudaGetLastError());
   note_launch();

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kLnThreads)
 ln_fwd_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int64_t sc, int T_img, int C,
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               __nv_bfloat16* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
+  pdl_prologue();
   extern __shared__ float tile[];  // [kLnTok][C + 1]
   const int ldt = C + 1;
   const int b = blockIdx.y;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256)
 ln_fwd_rows_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img, int64_t T,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    TOut* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
+  pdl_prologue();
   constexpr int C = 64 * NCH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(256)
 ln_fwd_multirow_kernel(const TIn* __restrict__ x, int64_t sb, int64_t st, int T_img, int64_t T,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                        TOut* __restrict__ xn, float* __restrict__ stats, float* __restrict__ x_copy) {
+  pdl_prologue();
   constexpr int C = 64 * NCH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ gamma, const float* __restrict__ dres, float* __restrict__ dx,
               __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, int T) {
+  pdl_prologue();
   constexpr int C = 64 * NCH;
   __shared__ __align__(16) float red[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -346,6 +350,7 @@ ln_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out, int T, int N, int rows_per_cta) {
+  pdl_prologue();
   __shared__ __align__(16) float red[256][8];
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const int r0 = blockIdx.y * rows_per_cta;
@@ -397,6 +402,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ out,
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  pdl_prologue();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
@@ -413,6 +419,7 @@ struct Cast4 {
   long long n[4];
 };
 __global__ void __launch_bounds__(256) cast4_bf16_kernel(const Cast4 c) {
+  pdl_prologue();
   const float* __restrict__ src = c.src[blockIdx.y];
   __nv_bfloat16* __restrict__ dst = c.dst[blockIdx.y];
   const long long n = c.n[blockIdx.y];
@@ -441,6 +448,7 @@ __global__ void __launch_bounds__(256) cast4_bf16_kernel(const Cast4 c) {
 // stand-alone window gather / scatter / mask (bit-exact index tests)
 // ------------------------------------------------------------------------------------------------
 __global__ void window_gather_kernel(const float* __restrict__ x, float* __restrict__ win, WindowGeom gm, int C) {
+  pdl_prologue();
   const int bw = blockIdx.x;  // b * nW + window
   const int b = bw / gm.nW, w = bw - b * gm.nW;
   const int N = gm.ws * gm.ws;
@@ -452,6 +460,7 @@ __global__ void window_gather_kernel(const float* __restrict__ x, float* __restr
   }
 }
 __global__ void window_scatter_kernel(const float* __restrict__ win, float* __restrict__ x, WindowGeom gm, int C) {
+  pdl_prologue();
   const int bw = blockIdx.x;
   const int b = bw / gm.nW, w = bw - b * gm.nW;
   const int N = gm.ws * gm.ws;
@@ -462,6 +471,7 @@ __global__ void window_scatter_kernel(const float* __restrict__ win, float* __re
   }
 }
 __global__ void shift_mask_kernel(float* __restrict__ mask, WindowGeom gm) {
+  pdl_prologue();
   const int w = blockIdx.x;
   const int N = gm.ws * gm.ws;
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
@@ -479,6 +489,7 @@ __global__ void shift_mask_kernel(float* __restrict__ mask, WindowGeom gm) {
 template <typename T, bool INVERSE>
 __global__ void __launch_bounds__(256)
 pixel_shuffle_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int H, int W, int C) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t npix = static_cast<int64_t>(B) * H * W;
   const int Cq = C >> 2;
@@ -541,9 +552,9 @@ int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, i
 #define CRF_LNF(NCH)                                                                                                  \
   case NCH:                                                                                                           \
     if (gamma != nullptr)                                                                                             \
-      ln_fwd_rows_kernel<TIn, NCH, true><<<blocks, 256, 0, st>>>(xp, sb, st_, T_img, T, gamma, beta, eps, xnp, stats, x_copy); \
+      launch_pdl((ln_fwd_rows_kernel<TIn, NCH, true>), blocks, 256, 0, st, xp, sb, st_, T_img, T, gamma, beta, eps, xnp, stats, x_copy); \
     else                                                                                                              \
-      ln_fwd_rows_kernel<TIn, NCH, false><<<blocks, 256, 0, st>>>(xp, sb, st_, T_img, T, nullptr, nullptr, eps, xnp, nullptr, x_copy); \
+      launch_pdl((ln_fwd_rows_kernel<TIn, NCH, false>), blocks, 256, 0, st, xp, sb, st_, T_img, T, nullptr, nullptr, eps, xnp, nullptr, x_copy); \
     break;
     switch (C / 64) {
       CRF_LNF(1) CRF_LNF(2) CRF_LNF(3) CRF_LNF(4) CRF_LNF(5) CRF_LNF(6) CRF_LNF(7) CRF_LNF(8) CRF_LNF(9) CRF_LNF(10)
@@ -558,12 +569,12 @@ int launch_ln_fwd_t(const void* x, int64_t sb, int64_t st_, int64_t sc, int B, i
   if (gamma != nullptr) {
     auto k = ln_fwd_kernel<TIn, true>;
     CRF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k<<<grid, kLnThreads, smem, st>>>(reinterpret_cast<const TIn*>(x), sb, st_, sc, T_img, C, gamma, beta, eps,
+    launch_pdl(k, grid, kLnThreads, smem, st, reinterpret_cast<const TIn*>(x), sb, st_, sc, T_img, C, gamma, beta, eps,
                                       reinterpret_cast<__nv_bfloat16*>(xn), stats, x_copy);
   } else {
     auto k = ln_fwd_kernel<TIn, false>;
     CRF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k<<<grid, kLnThreads, smem, st>>>(reinterpret_cast<const TIn*>(x), sb, st_, sc, T_img, C, nullptr, nullptr, eps,
+    launch_pdl(k, grid, kLnThreads, smem, st, reinterpret_cast<const TIn*>(x), sb, st_, sc, T_img, C, nullptr, nullptr, eps,
                                       reinterpret_cast<__nv_bfloat16*>(xn), nullptr, x_copy);
   }
   CRF_CUDA(cudaGetLastError());
@@ -618,7 +629,7 @@ int launch_ln_bwd(const float* g, const float* x, const float* stats, const floa
     }                                                                                                        \
     int blocks = (T + 7) / 8;                                                                                \
     if (blocks > sms * occ) blocks = sms * occ;                                                              \
-    ln_bwd_kernel<NCH><<<blocks, 256, 0, st>>>(g, x, stats, gamma, dres, dx, dxb, dgamma, dbeta, T);         \
+    launch_pdl((ln_bwd_kernel<NCH>), blocks, 256, 0, st, g, x, stats, gamma, dres, dx, dxb, dgamma, dbeta, T);         \
     break;                                                                                                   \
   }
   switch (C / 64) {
@@ -652,6 +663,7 @@ template <int NCH, typename TOut>
 __global__ void __launch_bounds__(256)
 layernorm_ps_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                         float eps, TOut* __restrict__ y, float* __restrict__ stats, int T, int H, int W) {
+  pdl_prologue();
   constexpr int C = 64 * NCH, C4 = C / 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * 8;
@@ -695,6 +707,7 @@ __global__ void __launch_bounds__(256)
 layernorm_ps_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ x, const float* __restrict__ stats,
                         const float* __restrict__ gamma, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16,
                         float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int H, int W) {
+  pdl_prologue();
   constexpr int C = 64 * NCH, C4 = C / 4;
   __shared__ float red[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -782,10 +795,10 @@ int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, 
 #define CRF_LNS(NCH)                                                                                                   \
   case NCH:                                                                                                            \
     if (y_dtype == CRF_DT_F32)                                                                                         \
-      ln_fwd_rows_kernel<float, NCH, true, float><<<blocks, 256, 0, st>>>(x, 0, C, T, T, gamma, beta, eps,             \
+      launch_pdl((ln_fwd_rows_kernel<float, NCH, true, float>), blocks, 256, 0, st, x, 0, C, T, T, gamma, beta, eps,             \
                                                                             reinterpret_cast<float*>(y), stats, nullptr); \
     else                                                                                                               \
-      ln_fwd_rows_kernel<float, NCH, true, __nv_bfloat16><<<blocks, 256, 0, st>>>(                                     \
+      launch_pdl((ln_fwd_rows_kernel<float, NCH, true, __nv_bfloat16>), blocks, 256, 0, st,                                      \
           x, 0, C, T, T, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y), stats, nullptr);                       \
     break;
   switch (C / 64) {
@@ -813,10 +826,10 @@ int launch_layernorm_bwd(const void* g, int g_dtype, const float* x, const float
 #define CRF_LNSB(NCH)                                                                                                  \
   case NCH:                                                                                                            \
     if (g_dtype == CRF_DT_F32)                                                                                         \
-      ln_bwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), x, stats, gamma, nullptr,   \
+      launch_pdl((ln_bwd_kernel<NCH, float>), blocks, 256, 0, st, reinterpret_cast<const float*>(g), x, stats, gamma, nullptr,   \
                                                         dx, dxb, dgamma, dbeta, T);                                    \
     else                                                                                                               \
-      ln_bwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), x, stats,    \
+      launch_pdl((ln_bwd_kernel<NCH, __nv_bfloat16>), blocks, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(g), x, stats,    \
                                                                 gamma, nullptr, dx, dxb, dgamma, dbeta, T);            \
     break;
   switch (C / 64) {
@@ -845,10 +858,10 @@ int launch_layernorm_ps_fwd(const float* x, const float* gamma, const float* bet
 #define CRF_LPS(NCH)                                                                                                    \
   case NCH:                                                                                                             \
     if (y_dtype == CRF_DT_F32)                                                                                          \
-      layernorm_ps_fwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, reinterpret_cast<float*>(y), stats, \
+      launch_pdl((layernorm_ps_fwd_kernel<NCH, float>), blocks, 256, 0, st, x, gamma, beta, eps, reinterpret_cast<float*>(y), stats, \
                                                                    T, H, W);                                            \
     else                                                                                                                \
-      layernorm_ps_fwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(x, gamma, beta, eps,                          \
+      launch_pdl((layernorm_ps_fwd_kernel<NCH, __nv_bfloat16>), blocks, 256, 0, st, x, gamma, beta, eps,                          \
                                                                            reinterpret_cast<__nv_bfloat16*>(y), stats, T, H, W); \
     break;
   switch (C / 64) {
@@ -878,10 +891,10 @@ int launch_layernorm_ps_bwd(const void* g, int g_dtype, const float* x, const fl
 #define CRF_LPB(NCH)                                                                                                    \
   case NCH:                                                                                                             \
     if (g_dtype == CRF_DT_F32)                                                                                          \
-      layernorm_ps_bwd_kernel<NCH, float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(g), x, stats, gamma, dx, \
+      launch_pdl((layernorm_ps_bwd_kernel<NCH, float>), blocks, 256, 0, st, reinterpret_cast<const float*>(g), x, stats, gamma, dx, \
                                                                    dxb, dgamma, dbeta, T, H, W);                        \
     else                                                                                                                \
-      layernorm_ps_bwd_kernel<NCH, __nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), x,  \
+      launch_pdl((layernorm_ps_bwd_kernel<NCH, __nv_bfloat16>), blocks, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(g), x,  \
                                                                            stats, gamma, dx, dxb, dgamma, dbeta, T, H, W); \
     break;
   switch (C / 64) {
@@ -909,11 +922,11 @@ int launch_pixel_shuffle_nhwc(const void* src, void* dst, int dtype, int B, int 
   KernelTimer tm(st, 0.0, 2.0 * npix * C * esz, "pixel_%sshuffle_B%d_%dx%d_C%d", inverse ? "un" : "", B, H, W, C);
   const unsigned nb = static_cast<unsigned>(blocks);
   if (dtype == CRF_DT_F32) {
-    if (inverse) pixel_shuffle_nhwc_kernel<float, true><<<nb, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), B, H, W, C);
-    else pixel_shuffle_nhwc_kernel<float, false><<<nb, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), B, H, W, C);
+    if (inverse) launch_pdl((pixel_shuffle_nhwc_kernel<float, true>), nb, 256, 0, st, reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), B, H, W, C);
+    else launch_pdl((pixel_shuffle_nhwc_kernel<float, false>), nb, 256, 0, st, reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), B, H, W, C);
   } else {
-    if (inverse) pixel_shuffle_nhwc_kernel<__nv_bfloat16, true><<<nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C);
-    else pixel_shuffle_nhwc_kernel<__nv_bfloat16, false><<<nb, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C);
+    if (inverse) launch_pdl((pixel_shuffle_nhwc_kernel<__nv_bfloat16, true>), nb, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C);
+    else launch_pdl((pixel_shuffle_nhwc_kernel<__nv_bfloat16, false>), nb, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), B, H, W, C);
   }
   CRF_CUDA(cudaGetLastError());
   note_launch();
@@ -938,7 +951,7 @@ int launch_colsum_bf16(const void* g, float* out, int T, int N, cudaStream_t st)
   if (rows < 8 * by) rows = 8 * by;
   gy = (T + rows - 1) / rows;
   KernelTimer tm(st, 0.0, 2.0 * T * N, "colsum_T%d_N%d", T, N);
-  colsum_bf16_kernel<<<dim3(gx, gy), dim3(bx, by), 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
+  launch_pdl(colsum_bf16_kernel, dim3(gx, gy), dim3(bx, by), 0, st, reinterpret_cast<const __nv_bfloat16*>(g), out, T, N, rows);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;
@@ -948,7 +961,7 @@ int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
   const int64_t threads = (n + 3) / 4;
   KernelTimer tm(st, 0.0, 6.0 * n, "cast_bf16_n%lld", static_cast<long long>(n));
-  cast_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+  launch_pdl(cast_bf16_kernel, static_cast<unsigned>((threads + 255) / 256), 256, 0, st, 
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   CRF_CUDA(cudaGetLastError());
   note_launch();
@@ -972,7 +985,7 @@ int launch_cast4_bf16(const float* const src[4], void* const dst[4], const long 
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   KernelTimer tm(st, 0.0, 6.0 * total, "cast4_bf16_n%lld", total);
-  cast4_bf16_kernel<<<dim3(static_cast<unsigned>(gx), 4), 256, 0, st>>>(c);
+  launch_pdl(cast4_bf16_kernel, dim3(static_cast<unsigned>(gx), 4), 256, 0, st, c);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

@@ -91,6 +91,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmXn,
                      const __grid_constant__ CUtensorMap tmPre, const __grid_constant__ CUtensorMap tmAct,
                      const MlpArgs a) {
+  pdl_launch_dependents();
   using PL = MlpPlan<C>;
   constexpr int NCH = PL::NCH, NJ = PL::NJ, NSUB = PL::NSUB, kS1 = PL::kS1, kS2 = PL::kS2, kXnBufs = PL::kXnBufs,
                 kYBufs = PL::kYBufs;
@@ -158,6 +159,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr_gen;
   const uint32_t tmem_pre = tmem_base, tmem_y = tmem_base + kPreBufs * HC;
 
@@ -522,7 +524,7 @@ int launch_mlp_c(const crf_mlp_args& m, cudaStream_t st) {
   const double tc = static_cast<double>(m.T) * C;
   KernelTimer timer(st, 16.0 * tc * C, tc * (8.0 + (m.training ? 18.0 : 0.0)) + 16.0 * C * C, "mlp_fused_fwd_T%d_C%d%s",
                  m.T, C, m.training ? "" : "_infer");
-  kern<<<grid, kThreads, PL::kSmemBytes, st>>>(tmW1, tmW2, tmY, tmXn, tmPre, tmAct, a);
+  launch_pdl(kern, grid, kThreads, PL::kSmemBytes, st, tmW1, tmW2, tmY, tmXn, tmPre, tmAct, a);
   CRF_CUDA(cudaGetLastError());
   note_launch();
   return 0;

@@ -131,6 +131,21 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// Programmatic dependent launch (launch_pdl in crf_host.h).  First statement of every kernel: let the NEXT kernel of the
+// stream be scheduled as soon as all CTAs of this grid have started (its CTAs then park in their own griddepcontrol.wait
+// until this grid has completed and its memory is visible), and wait for the PREVIOUS grid the same way.  Nothing of a
+// kernel runs before the wait, so only launch latency and CTA scheduling overlap the previous kernel's tail; both
+// instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+// The tcgen05 kernels split the two: barrier init, TMEM allocation, descriptor prefetch and the copies of PARAMETERS
+// (biases, LayerNorm weights, the relative-position table: written by the optimiser, many full kernel boundaries earlier)
+// into shared memory run BEFORE pdl_wait(), i.e. under the previous kernel's tail; activations, bf16 weight copies and
+// everything else a neighbouring library kernel may have produced are only touched after it.
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {  // all but the N most recent groups have finished READING smem
