@@ -28,6 +28,7 @@
 
 #include "crf_host.h"
 #include "crf_ptx.cuh"
+#include "crf_sched.h"
 
 namespace crf {
 
@@ -379,13 +380,8 @@ int launch_c(const void* dY, const void* W, int K, const float* x, const float* 
   // so that the tiles fill whole rounds of the persistent grid (T = 38400: 300 tiles of 128 rows are 2.03 rounds on 148
   // SMs, i.e. 3; 437 tiles of 88 rows are 2.95 rounds of a shorter tile: -31 % row-time).
   const int sms = num_sms(device);
-  int tm = TM;
+  int tm = balanced_tile_rows(T, sms);
   {
-    const int g0 = (T + TM - 1) / TM < sms ? (T + TM - 1) / TM : sms;
-    const int rows_per_cta = (T + g0 - 1) / g0;
-    const int n = (rows_per_cta + TM - 1) / TM;
-    tm = (((rows_per_cta + n - 1) / n) + 7) & ~7;
-    if (tm > TM) tm = TM;
     static const bool fixed = getenv("CRF_LNBWD_TM128") != nullptr;
     if (fixed) tm = TM;
   }

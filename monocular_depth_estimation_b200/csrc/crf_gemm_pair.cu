@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "crf_gemm_epi.cuh"
+#include "crf_sched.h"
 
 namespace crf {
 
@@ -43,43 +44,7 @@ static_assert(kSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
 //           then runs the ordinary epilogue).  A contributor piece is always the FIRST piece of its pair and waits for
 //           nothing, an owner piece is the LAST of its pair, so the flags are long set when they are needed and no pair
 //           ever waits on a pair that waits (CTAs are dispatched in index order; all 74 pairs are resident).
-struct Piece {
-  int t, kc0, kc1;
-};
-// range boundary of pair p, snapped to a tile boundary when it would leave a piece of fewer than `snap` K chunks
-__device__ __forceinline__ int sk_bound(int p, int npairs, int total, int nk, int snap) {
-  int b = static_cast<int>(static_cast<long long>(p) * total / npairs);
-  const int rem = b % nk;
-  if (rem < snap) b -= rem;
-  else if (nk - rem < snap) b += nk - rem;
-  return b;
-}
-struct PieceIter {
-  int nk, tiles, pair, npairs, streamk, w, w1, i;
-  __device__ PieceIter(int nk_, int tiles_, int pair_, int npairs_, int streamk_, int snap)
-      : nk(nk_), tiles(tiles_), pair(pair_), npairs(npairs_), streamk(streamk_), w(0), w1(0), i(0) {
-    if (streamk) {
-      w = sk_bound(pair, npairs, tiles * nk, nk, snap);
-      w1 = sk_bound(pair + 1, npairs, tiles * nk, nk, snap);
-    }
-  }
-  __device__ bool next(Piece& p) {
-    if (!streamk) {
-      const int t = pair + i * npairs;
-      if (t >= tiles) return false;
-      ++i;
-      p.t = t; p.kc0 = 0; p.kc1 = nk;
-      return true;
-    }
-    if (w >= w1) return false;
-    p.t = w / nk;
-    p.kc0 = w - p.t * nk;
-    p.kc1 = min(nk, p.kc0 + (w1 - w));
-    w += p.kc1 - p.kc0;
-    return true;
-  }
-};
-constexpr int kMaxContrib = 8;
+// (Piece, PieceIter, sk_bound, sk_contributors: crf_sched.h -- compiled on the host by tests/test_sched_host.py)
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -214,7 +179,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int aux_cnt = 0;
     // stream-K partial slots: [pair][rank][group] x (32 column quads x 128 rows x float4) -- a warp's accesses are contiguous
     constexpr int kSlotFloats = 128 * 128;
-    const int total_units = total_tiles * nk_all;
     PieceIter pit(nk_all, total_tiles, pair, npairs, streamk, snap);
     Piece pc;
     for (int i = 0; pit.next(pc); ++i) {
@@ -233,19 +197,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int n_contrib = 0;
       const float* contrib[kMaxContrib];
       if (head) {
-        const int tile_end = (t + 1) * nk_all;
-        int pos = t * nk_all + pc.kc1, q = pair + 1;
-        while (pos < tile_end && q < npairs && n_contrib < kMaxContrib) {
-          const int q0 = sk_bound(q, npairs, total_units, nk_all, snap), q1 = sk_bound(q + 1, npairs, total_units, nk_all, snap);
-          if (q1 > q0) {  // (empty ranges hold nothing)
-            const int slot = (q * 2 + static_cast<int>(rank)) * 2 + e;
-            if (r == 0) {
-              while (ld_acquire_gpu(sk_flags + slot) == 0u) __nanosleep(64);
-            }
-            contrib[n_contrib++] = sk_ws + static_cast<size_t>(slot) * kSlotFloats;
-            pos = min(q1, tile_end);
+        int q[kMaxContrib];
+        n_contrib = sk_contributors(pair, npairs, total_tiles, nk_all, snap, t, pc.kc1, q);
+        if (n_contrib < 0) n_contrib = 0;   // (the host only selects stream-K for shapes where this cannot happen)
+        for (int k = 0; k < n_contrib; ++k) {
+          const int slot = (q[k] * 2 + static_cast<int>(rank)) * 2 + e;
+          if (r == 0) {
+            while (ld_acquire_gpu(sk_flags + slot) == 0u) __nanosleep(64);
           }
-          ++q;
+          contrib[k] = sk_ws + static_cast<size_t>(slot) * kSlotFloats;
         }
       }
       mbar_wait(tfull_bar(a), (i >> 1) & 1);

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "crf_gemm_epi.cuh"
+#include "crf_sched.h"
 
 namespace crf {
 
@@ -496,13 +497,8 @@ int launch_mlp_c(const crf_mlp_args& m, cudaStream_t st) {
   // tm chosen so that the tiles fill whole rounds of the persistent grid (T = 38400: 300 tiles of 128 rows = 2.03 rounds
   // on 148 SMs, i.e. 3 rounds; 437 tiles of 88 rows = 2.95 rounds of a shorter tile).  CRF_MLP_TM128=1: always 128.
   const int sms = num_sms(m.device);
-  int tm = TM;
+  int tm = balanced_tile_rows(m.T, sms);
   {
-    const int g0 = (m.T + TM - 1) / TM < sms ? (m.T + TM - 1) / TM : sms;
-    const int rows_per_cta = (m.T + g0 - 1) / g0;
-    const int n = (rows_per_cta + TM - 1) / TM;
-    tm = (((rows_per_cta + n - 1) / n) + 7) & ~7;
-    if (tm > TM) tm = TM;
     static const bool fixed = getenv("CRF_MLP_TM128") != nullptr;
     if (fixed) tm = TM;
   }
