@@ -66,16 +66,17 @@ __device__ __forceinline__ void epi_group32(const uint32_t (&acc)[32], const Epi
     add_bias32(v, ep.bias, n);
     if (ep.store_out0) store_bf16_32(o0, r, half * 4, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 16; ++j) gelu_erf2(v[2 * j], v[2 * j + 1]);   // packed fp32x2, bit-identical to gelu_erf
     store_bf16_32(xb, r, half * 4, v);
   } else if constexpr (EPI == CRF_EPI_MUL_DGELU) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 p = *reinterpret_cast<const uint4*>(xb + sw128_offset(r, half * 4 + j));
-      v[8 * j + 0] *= dgelu_erf(bf16_lo(p.x)); v[8 * j + 1] *= dgelu_erf(bf16_hi(p.x));
-      v[8 * j + 2] *= dgelu_erf(bf16_lo(p.y)); v[8 * j + 3] *= dgelu_erf(bf16_hi(p.y));
-      v[8 * j + 4] *= dgelu_erf(bf16_lo(p.z)); v[8 * j + 5] *= dgelu_erf(bf16_hi(p.z));
-      v[8 * j + 6] *= dgelu_erf(bf16_lo(p.w)); v[8 * j + 7] *= dgelu_erf(bf16_hi(p.w));
+      const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)   // packed fp32x2: same operations, same order as dgelu_erf on each value
+        f2_unpack(f2_mul(f2_pack(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]), dgelu_erf2(bf16_lo(pw[q]), bf16_hi(pw[q]))),
+                  v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
     }
     store_bf16_32(o0, r, half * 4, v);
   }

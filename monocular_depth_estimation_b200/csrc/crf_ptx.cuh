@@ -460,6 +460,27 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   f2_unpack(f2_mul(X, f2_pack(rcp_approx(d0), rcp_approx(d1))), x0, x1);
 }
 
+// gelu'(x) on a pair of values with packed arithmetic: the operations of dgelu_erf in the same order (bit-identical
+// results), ~11 instead of ~19 issue slots per element -- the d fc2 x gelu' epilogue is issue-bound (16 epilogue warps at
+// 52 % issue utilisation cover 87 us at the 1/4 scale against an HBM time of 55 us).  Returns (gelu'(x0), gelu'(x1)) packed.
+__device__ __forceinline__ uint64_t dgelu_erf2(float x0, float x1) {
+  const uint64_t X = f2_pack(x0, x1);
+  float t0, t1;
+  f2_unpack(f2_mul(X, X), t0, t1);
+  const uint64_t T = f2_pack(fminf(t0, 25.0f), fminf(t1, 25.0f));
+  uint64_t R = f2_fma(f2_pack(0.0010142630f, 0.0010142630f), T, f2_pack(-0.10677572f, -0.10677572f));
+  R = f2_fma(R, T, f2_pack(-2.3011212f, -2.3011212f));
+  float e0, e1;
+  f2_unpack(f2_mul(X, R), e0, e1);
+  float d0, d1;
+  f2_unpack(f2_add(f2_pack(ex2_approx(e0), ex2_approx(e1)), f2_pack(1.0f, 1.0f)), d0, d1);
+  const uint64_t S = f2_pack(rcp_approx(d0), rcp_approx(d1));                       // s = gelu_cdf(x)
+  uint64_t WP = f2_fma(f2_pack(-0.0035151686f, -0.0035151686f), T, f2_pack(0.22203402f, 0.22203402f));
+  WP = f2_fma(WP, T, f2_pack(1.5950157f, 1.5950157f));
+  const uint64_t S1 = f2_fma(S ^ 0x8000000080000000ull, S, S);                       // fmaf(-s, s, s)
+  return f2_fma(f2_mul(X, WP), S1, S);                                               // fmaf(x * wp, s (1 - s), s)
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
