@@ -578,14 +578,15 @@ def test_window_attention_standalone_matches_oracle(with_mask):
     assert not bad, f"{bad}\nall: {errs}"
 
 
+@pytest.mark.parametrize("C,nH", [(64, 2), (128, 4), (256, 8)])
 @pytest.mark.parametrize("B,H,W", [(1, 1, 1), (1, 3, 5), (1, 7, 7), (3, 8, 13), (2, 6, 50), (5, 14, 7), (1, 20, 29)])
-def test_ragged_geometries_vs_oracle(B, H, W):
+def test_ragged_geometries_vs_oracle(B, H, W, C, nH):
     """Edge geometries: maps smaller than one window (all-pad windows but one), exact multiples of 7 (no padding),
     odd numbers of windows (the last window pair is half empty), token counts that are not multiples of the 128-row
-    GEMM tile.  Two blocks (shift 0 and 3), fwd + bwd, vs the fp32 oracle."""
+    GEMM tile (nor of the 8-row granularity of the balanced tiles).  Two blocks (shift 0 and 3), fwd + bwd, vs the fp32
+    oracle.  C = 64 runs the unfused kernels, C = 128 / 256 the fused MLP forward and the fused d.LN' kernels."""
     pkg = _pkg()
     torch.manual_seed(B * 1000 + H * 31 + W)
-    C, nH = 64, 2
     layer = pkg.BasicCRFLayer(dim=C, depth=2, num_heads=nH, v_dim=C).to(DEV)
     with torch.no_grad():
         for p in layer.parameters():
@@ -605,7 +606,7 @@ def test_ragged_geometries_vs_oracle(B, H, W):
     for i, blk in enumerate(layer.blocks):
         for k, p in blk.named_parameters():
             errs[f"{i}.{k}"] = rel_l2(p.grad, blocks[i][k].grad)
-    _report(f"ragged B{B} {H}x{W}", errs)
+    _report(f"ragged B{B} {H}x{W} C{C}", errs)
     bad = {k: e for k, e in errs.items() if not e < TOL}
     assert not bad, f"{bad}\nall: {errs}"
 
