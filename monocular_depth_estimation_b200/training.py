@@ -180,6 +180,24 @@ def prefetch_to_device(batches, device, memory_format=torch.contiguous_format):
         yield cur
 
 
+def _dense(t):
+    """Non-overlapping and dense in memory (any permutation of a contiguous layout, e.g. channels-last)."""
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
+        return True
+    sizes_strides = sorted(((st, sz) for sz, st in zip(t.size(), t.stride()) if sz > 1))
+    expect = 1
+    for st, sz in sizes_strides:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+def _same_layout(a, b):
+    """Same element order in memory: equal strides on every dimension longer than 1."""
+    return a.size() == b.size() and all(sa == sb for n, sa, sb in zip(a.size(), a.stride(), b.stride()) if n > 1)
+
+
 class LibAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr) of the reference loop (src/train.py:41, :108) as the library's multi-tensor step
     (crf_adam_step: 80 tensors per launch, pointers passed as launch arguments) instead of torch's multi-tensor launches;
@@ -207,8 +225,8 @@ class LibAdam(torch.optim.Optimizer):
     def _init_group(self, group):
         ps = [p for p in group["params"] if p.requires_grad]
         for p in ps:
-            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                raise RuntimeError("LibAdam: parameters must be contiguous CUDA fp32 tensors (there is no CPU path)")
+            if not (p.is_cuda and p.dtype == torch.float32 and _dense(p)):
+                raise RuntimeError("LibAdam: parameters must be dense CUDA fp32 tensors (there is no CPU path)")
         missing = [p for p in ps if "exp_avg" not in self.state[p]]
         if missing:
             dev = missing[0].device
@@ -220,8 +238,10 @@ class LibAdam(torch.optim.Optimizer):
             o = 0
             for p, n in zip(missing, sizes):
                 self.state[p]["step"] = group["_step"]
-                self.state[p]["exp_avg"] = flat_m[o:o + p.numel()].view_as(p)
-                self.state[p]["exp_avg_sq"] = flat_v[o:o + p.numel()].view_as(p)
+                # the update is element-wise over memory: the moments take the parameter's own (dense) strides, so a
+                # channels-last convolution weight keeps its layout
+                self.state[p]["exp_avg"] = flat_m[o:o + p.numel()].as_strided(p.size(), p.stride())
+                self.state[p]["exp_avg_sq"] = flat_v[o:o + p.numel()].as_strided(p.size(), p.stride())
                 o += n
         return ps
 
@@ -248,7 +268,10 @@ class LibAdam(torch.optim.Optimizer):
                 for p in have:
                     self.state[p]["step"] = group["_step"]
                     for k in ("exp_avg", "exp_avg_sq"):
-                        self.state[p][k] = self.state[p][k].to(device=p.device, dtype=torch.float32).contiguous()
+                        t = self.state[p][k].to(device=p.device, dtype=torch.float32)
+                        if not _same_layout(t, p):
+                            t = torch.empty_strided(p.size(), p.stride(), dtype=torch.float32, device=p.device).copy_(t)
+                        self.state[p][k] = t
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -266,8 +289,10 @@ class LibAdam(torch.optim.Optimizer):
             recs = (L.AdamTensor * len(ps))()
             for r, p in zip(recs, ps):
                 g = p.grad
-                if g.dtype != torch.float32 or not g.is_contiguous() or g.device != dev:
-                    raise RuntimeError("LibAdam: gradients must be contiguous fp32 tensors on the parameters' device")
+                if g.dtype != torch.float32 or g.device != dev:
+                    raise RuntimeError("LibAdam: gradients must be fp32 tensors on the parameters' device")
+                if not _same_layout(g, p):   # rare: re-lay the gradient out like the parameter (element-wise update)
+                    g = torch.empty_strided(p.size(), p.stride(), dtype=torch.float32, device=dev).copy_(g)
                 st = self.state[p]
                 r.p, r.g, r.m, r.v, r.n = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
             b1, b2 = group["betas"]

@@ -723,13 +723,18 @@ def test_lib_adam_matches_torch_adam():
     base = torch.randn(40, device=DEV)
     ours = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
     ours.append(torch.nn.Parameter(base[1:34]))                    # 4-byte-aligned view: scalar path
+    # dense but not "contiguous": channels-last convolution weights (3x3, and 1x1 whose size-1 strides are arbitrary)
+    ours.append(torch.nn.Parameter(torch.randn(16, 8, 3, 3, device=DEV).contiguous(memory_format=torch.channels_last)))
+    ours.append(torch.nn.Parameter(torch.randn(24, 40, 1, 1, device=DEV).contiguous(memory_format=torch.channels_last)))
     ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
     oa = LibAdam(ours, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
     ob = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
     for step in range(6):
-        for a, b in zip(ours, ref):
+        for k, (a, b) in enumerate(zip(ours, ref)):
             g = torch.randn_like(a) * (10.0 ** (step - 3))
             a.grad, b.grad = g.clone(), g.clone()
+            if a.dim() == 4 and step % 2 == 1:   # a gradient laid out differently from its parameter is re-laid out
+                a.grad = g.contiguous().clone()
         oa.step()
         ob.step()
     torch.cuda.synchronize()
