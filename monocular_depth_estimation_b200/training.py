@@ -205,10 +205,11 @@ class LibAdam(torch.optim.Optimizer):
     the reference's checkpoints load.  The step counter lives on the device, hence a CUDA graph that captured the step
     keeps counting on replay.  CUDA fp32 parameters only.
 
-    Status: the element update is verified on the host against torch.optim.Adam (tests/test_adam_host.py) and the kernel
-    on a B200 against the same update (tools/hwcheck, profiles/r01_hwcheck.txt: bit-identical, incl. an unaligned
-    gradient view and the device step counter); its speed and its capture in a CUDA graph have not been measured yet --
-    opt-in (`bench.py --lib-adam`); the default remains torch's fused Adam."""
+    Status: the element update is verified on the host against torch.optim.Adam (tests/test_adam_host.py) and on a B200
+    against torch.optim.Adam over several steps incl. channels-last weights, an unaligned view and state_dict round trips
+    (tests/test_gpu_stages.py::test_lib_adam_matches_torch_adam, 1e-5); measured in the training step (round 2): 0.28 ms
+    for the model's 302 tensors, 13.9 ms per step against 14.15-14.5 with torch's fused Adam, same loss trajectory --
+    `bench.py` uses it by default (`--torch-adam` for torch's)."""
 
     CHUNK = 16384   # elements per CTA (64 KB of each of p, g, m, v)
 
