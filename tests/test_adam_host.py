@@ -82,3 +82,19 @@ def test_lib_adam_refuses_cpu_parameters():
     w.grad = torch.randn(8)
     with pytest.raises(RuntimeError, match="CUDA"):
         LibAdam([w], lr=1e-4).step()
+
+
+def test_dense_and_same_layout_helpers():
+    """LibAdam updates memory element-wise: parameters only need to be dense (any permutation of a contiguous layout,
+    e.g. channels-last convolution weights), and a gradient must have the parameter's element order -- strides of
+    size-1 dimensions do not matter (1x1 convolution weights in channels-last report different ones)."""
+    from monocular_depth_estimation_b200.training import _dense, _same_layout
+    a = torch.randn(6, 4, 3, 3)
+    cl = a.contiguous(memory_format=torch.channels_last)
+    assert _dense(a) and _dense(cl) and _dense(a.permute(2, 0, 3, 1)) and _dense(torch.randn(5)[:3])
+    assert not _dense(a[:, ::2]) and not _dense(torch.randn(10)[::2]) and not _dense(a[:, :, :2])
+    assert _same_layout(a, a.clone()) and not _same_layout(a, cl) and _same_layout(cl, cl.clone())
+    w11 = torch.randn(24, 40, 1, 1)
+    w11_cl = w11.contiguous(memory_format=torch.channels_last)      # same element order, different size-1 strides
+    assert _same_layout(w11, w11_cl) and _dense(w11_cl)
+    assert not _same_layout(a, torch.randn(6, 4, 3, 2))
