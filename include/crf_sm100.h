@@ -132,7 +132,8 @@ int crf_block_bwd(const crf_block_desc* d, const crf_block_params* p, const void
  * newcrf_layers.py:430-431), in ONE call each way.  Compared with `depth` crf_block_* calls this converts v once,
  * hands the gradient between blocks in fp32 + bf16 without extra casts and accumulates dv inside the kernels.
  *   d      : descriptor of the layer's input x / v (the shift field is ignored; blocks after the first read the
- *            previous block's contiguous fp32 output)
+ *            previous block's contiguous fp32 output).  A v that already is bf16, token-major and contiguous is read
+ *            in place by both calls (no copy): it must then still be valid, unchanged, in crf_layer_bwd
  *   y      : (B, H*W, C) contiguous, f32, or bf16 when out_dtype == CRF_DT_BF16 (needs the closing norm)
  *   dy     : gradient of y in y's dtype; dx (B, H*W, C) contiguous in x's dtype (f32 or bf16); dv (B, H, W, C) f32
  *            (both overwritten)

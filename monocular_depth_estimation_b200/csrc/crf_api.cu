@@ -37,6 +37,13 @@ bool fused_lnbwd_enabled() {
   return on;
 }
 
+// v already is what the attention kernels read: bf16 rows, token-major, contiguous (the channels-last output of the
+// proj_v convolution under bf16 autocast) -- the layer then uses it in place instead of making the bf16 copy
+bool v_is_token_major_bf16(const crf_block_desc& d) {
+  return d.v_dtype == CRF_DT_BF16 && d.v_stride_c == 1 && d.v_stride_w == d.C &&
+         d.v_stride_h == static_cast<int64_t>(d.W) * d.C && d.v_stride_b == static_cast<int64_t>(d.H) * d.W * d.C;
+}
+
 bool x_is_plain(const crf_block_desc& d) {
   const int64_t T_img = static_cast<int64_t>(d.H) * d.W;
   return d.x_dtype == CRF_DT_F32 && d.x_stride_c == 1 && d.x_stride_t == d.C && d.x_stride_b == T_img * d.C;
@@ -427,7 +434,7 @@ int crf_layer_fwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
   const int T = d->B * d->H * d->W;
   const bool fp32 = d->precision == CRF_PREC_FP32;
   const void* vin = v;
-  if (!fp32) {
+  if (!fp32 && !v_is_token_major_bf16(*d)) {
     crf_block_desc d0 = *d;
     d0.v_preconverted = 0;
     if (crf_convert_v(&d0, v, S + L.vb, stream)) return 1;
@@ -459,7 +466,8 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
                   void* ws, size_t ws_bytes, void* stream) {
   if (check_layer(d, a)) return 1;
   CRF_CHECK(x && dy && saved && dx && dv && g && ws, "crf_layer_bwd: null pointer");
-  CRF_CHECK(d->precision != CRF_PREC_FP32 || v != nullptr, "crf_layer_bwd: the fp32 mode re-reads v");
+  CRF_CHECK((d->precision != CRF_PREC_FP32 && !v_is_token_major_bf16(*d)) || v != nullptr,
+            "crf_layer_bwd: the fp32 mode, and a bf16 token-major v (used in place), re-read v");
   CRF_CHECK(d->training, "crf_layer_bwd: forward was not run with training=1");
   const int with_norm = a->norm_w != nullptr;
   CRF_CHECK(!with_norm || (dnorm_w && dnorm_b), "crf_layer_bwd: gradient buffers of the closing norm are missing");
@@ -508,7 +516,8 @@ int crf_layer_bwd(const crf_block_desc* d, const crf_layer_args* a, const void* 
     void* dxo16 = i == 0 ? (dx_is_bf16 ? dx : nullptr)
                          : static_cast<void*>(Wk + W.mid_bf16[i & 1]);
     const bool fp32 = d->precision == CRF_PREC_FP32;
-    if (block_bwd_impl(&bd, a->params + i, xin, fp32 ? v : static_cast<const void*>(S + L.vb), g32, g16, S + L.blk[i], dxo,
+    const void* vin = (fp32 || v_is_token_major_bf16(*d)) ? v : static_cast<const void*>(S + L.vb);
+    if (block_bwd_impl(&bd, a->params + i, xin, vin, g32, g16, S + L.blk[i], dxo,
                        dxo16, dv, i == a->depth - 1 ? 0 : 1, g + i, Wk + W.blk,
                        fp32 ? precise_bwd_bytes(bd) : bwd_layout(bd).total, stream))
       return 1;
