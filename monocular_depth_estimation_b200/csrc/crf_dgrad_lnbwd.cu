@@ -6,7 +6,8 @@
 // i.e. the backward of `self.norm2(x)` / `self.norm1(x)` in CRFBlock.forward (/root/reference/src/newcrf_layers.py:208,255)
 // applied to the gradient coming out of fc1 / qk, plus the residual branch (`dres`).  Unfused, g is an fp32 (T, C)
 // tensor that one kernel writes and the next reads (158 MB per LayerNorm at the 1/4 scale); here a persistent CTA's output
-// tile spans whole rows (128 tokens x C columns), so the row reductions happen on the accumulator in TMEM:
+// tile spans whole rows (tm <= 128 tokens x C columns; tm balanced against the grid, crf_sched.h), so the row reductions
+// happen on the accumulator in TMEM:
 //
 //   warp 8        TMA producer of the A / B ring (A: 128 x 64 K-major tile of dY; B: 64 x C MN-major tile of W, from L2)
 //   warp 9        MMA issuer: tile i accumulates into TMEM buffer i % (512 / C)
